@@ -1,0 +1,475 @@
+// csfm_api.cu — the extern "C" surface declared in include/csfm.h.
+//
+// Host logic only: argument checks, host<->device staging for the host-pointer entry points,
+// workspace reuse, accounting. No algorithm lives here and nothing here can run a query on the
+// CPU: every path ends in a kernel launch from csfm_query.cu / csfm_build.cu / csfm_sa.cu.
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "csfm_host.hpp"
+
+namespace csfm {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int DeviceBuffer::ensure(size_t bytes) {
+  if (bytes <= cap) return CSFM_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(&p, want);
+  }
+  if (e != cudaSuccess) return fail(CSFM_ERR_NOMEM, std::string("cudaMalloc(workspace): ") + cudaGetErrorString(e));
+  cap = want;
+  return CSFM_OK;
+}
+void DeviceBuffer::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+DeviceGuard::DeviceGuard(int dev) {
+  if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+  ok = (cudaSetDevice(dev) == cudaSuccess);
+}
+DeviceGuard::~DeviceGuard() {
+  if (prev >= 0) cudaSetDevice(prev);
+}
+
+static int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(CSFM_ERR_CUDA, std::string("no usable CUDA device (this engine has no CPU fallback): ") +
+                                   cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(CSFM_ERR_INVALID, "device ordinal out of range");
+  return CSFM_OK;
+}
+
+static uint32_t stride_of(const csfm_params* p) { return p ? p->ssa_stride : 32u; }
+
+}  // namespace csfm
+
+using namespace csfm;
+
+extern "C" {
+
+const char* csfm_last_error(void) { return g_last_error.c_str(); }
+const char* csfm_version(void) { return "csfm-b200 0.1 (sm_100a)"; }
+
+int csfm_device_count(int* count) {
+  if (!count) return fail(CSFM_ERR_INVALID, "count is null");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(CSFM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return CSFM_OK;
+}
+
+int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_params* params, int device,
+                                uint32_t flags, csfm_index** out) {
+  if (!out) return fail(CSFM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n && !d_text) return fail(CSFM_ERR_INVALID, "text is null");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  const uint32_t stride = stride_of(params);
+  uint8_t* d_bwt = nullptr;
+  uint32_t *d_ssa = nullptr, *d_sa = nullptr;
+  uint64_t nsamp = 0;
+  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp,
+                           (flags & CSFM_BUILD_KEEP_SA) ? &d_sa : nullptr);
+  if (rc) return rc;
+  rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, stride, device, flags, out);
+  cudaFree(d_bwt);
+  cudaFree(d_ssa);
+  if (rc) {
+    cudaFree(d_sa);
+    return rc;
+  }
+  (*out)->d_sa = d_sa;
+  return CSFM_OK;
+}
+
+int csfm_build_from_text(const uint8_t* text, uint64_t n, const csfm_params* params, int device, uint32_t flags,
+                         csfm_index** out) {
+  if (!out) return fail(CSFM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (n && !text) return fail(CSFM_ERR_INVALID, "text is null");
+  if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  uint8_t* d_text = nullptr;
+  CSFM_CUDA(cudaMalloc(&d_text, n ? n : 1));
+  cudaError_t e = cudaMemcpy(d_text, text, n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d_text);
+    return fail(CSFM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  rc = csfm_build_from_text_device(d_text, n, params, device, flags, out);
+  cudaFree(d_text);
+  return rc;
+}
+
+int csfm_build_from_parts(const uint8_t* bwt, uint64_t n, const uint32_t* ssa, uint64_t nsamp, uint32_t ssa_stride,
+                          int device, uint32_t flags, csfm_index** out) {
+  if (!out) return fail(CSFM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if ((n && !bwt) || (nsamp && !ssa)) return fail(CSFM_ERR_INVALID, "null input");
+  if (ssa_stride == 0) return fail(CSFM_ERR_INVALID, "ssa_stride must be > 0");
+  if (nsamp != (n + ssa_stride - 1) / ssa_stride)
+    return fail(CSFM_ERR_INVALID, "nsamp must equal ceil(n / ssa_stride)");
+  if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  uint8_t* d_bwt = nullptr;
+  uint32_t* d_ssa = nullptr;
+  CSFM_CUDA(cudaMalloc(&d_bwt, n ? n : 1));
+  cudaError_t e = cudaMalloc(&d_ssa, nsamp ? nsamp * 4 : 4);
+  if (e == cudaSuccess) e = cudaMemcpy(d_bwt, bwt, n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nsamp) e = cudaMemcpy(d_ssa, ssa, nsamp * 4, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d_bwt);
+    cudaFree(d_ssa);
+    return fail(CSFM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, ssa_stride, device, flags, out);
+  cudaFree(d_bwt);
+  cudaFree(d_ssa);
+  return rc;
+}
+
+void csfm_destroy(csfm_index* idx) {
+  if (!idx) return;
+  DeviceGuard g(idx->device);
+  if (idx->stream) cudaStreamSynchronize(idx->stream);
+  if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
+  if (idx->d_sa) cudaFree(idx->d_sa);
+  idx->ws_in.release();
+  idx->ws_out.release();
+  idx->ws_tmp.release();
+  idx->ws_scan.release();
+  idx->ws_pos.release();
+  if (idx->d_counters) cudaFree(idx->d_counters);
+  if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
+  if (idx->ev0) cudaEventDestroy(idx->ev0);
+  if (idx->ev1) cudaEventDestroy(idx->ev1);
+  if (idx->stream) cudaStreamDestroy(idx->stream);
+  delete idx;
+}
+
+int csfm_info(const csfm_index* idx, csfm_index_info* out) {
+  if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
+  std::memset(out, 0, sizeof *out);
+  out->n = idx->h.n;
+  out->sigma = idx->h.sigma;
+  out->levels = idx->h.levels;
+  out->ssa_stride = idx->h.stride;
+  out->device = (uint32_t)idx->device;
+  out->nsamp = idx->h.nsamp;
+  out->blocks_per_level = idx->h.nblk;
+  out->blob_bytes = idx->blob_bytes;
+  out->has_sa = idx->d_sa != nullptr;
+  return CSFM_OK;
+}
+
+int csfm_get_C(const csfm_index* idx, uint32_t C[257]) {
+  if (!idx || !C) return fail(CSFM_ERR_INVALID, "null argument");
+  std::memcpy(C, idx->h.C, 257 * 4);
+  return CSFM_OK;
+}
+
+int csfm_get_ssa(const csfm_index* idx, uint32_t* out) {
+  if (!idx || (!out && idx->h.nsamp)) return fail(CSFM_ERR_INVALID, "null argument");
+  DeviceGuard g(idx->device);
+  if (idx->h.nsamp)
+    CSFM_CUDA(cudaMemcpy(out, idx->d_blob + idx->h.off_ssa, idx->h.nsamp * 4, cudaMemcpyDeviceToHost));
+  return CSFM_OK;
+}
+
+int csfm_get_sa(const csfm_index* idx, uint32_t* out) {
+  if (!idx || (!out && idx->h.n)) return fail(CSFM_ERR_INVALID, "null argument");
+  if (idx->h.n && !idx->d_sa) return fail(CSFM_ERR_INVALID, "suffix array not resident (build with CSFM_BUILD_KEEP_SA)");
+  DeviceGuard g(idx->device);
+  if (idx->h.n) CSFM_CUDA(cudaMemcpy(out, idx->d_sa, idx->h.n * 4, cudaMemcpyDeviceToHost));
+  return CSFM_OK;
+}
+
+int csfm_release_sa(csfm_index* idx) {
+  if (!idx) return fail(CSFM_ERR_INVALID, "null argument");
+  DeviceGuard g(idx->device);
+  if (idx->d_sa) cudaFree(idx->d_sa);
+  idx->d_sa = nullptr;
+  return CSFM_OK;
+}
+
+int csfm_extract_bwt(const csfm_index* cidx, uint8_t* out) {
+  csfm_index* idx = const_cast<csfm_index*>(cidx);
+  if (!idx || (!out && idx->h.n)) return fail(CSFM_ERR_INVALID, "null argument");
+  if (idx->h.n == 0) return CSFM_OK;
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  int rc = idx->ws_out.ensure(idx->h.n);
+  if (rc) return rc;
+  rc = extract_bwt_device(idx, idx->ws_out.as<uint8_t>(), idx->stream);
+  if (rc) return rc;
+  CSFM_CUDA(cudaMemcpyAsync(out, idx->ws_out.p, idx->h.n, cudaMemcpyDeviceToHost, idx->stream));
+  CSFM_CUDA(cudaStreamSynchronize(idx->stream));
+  return CSFM_OK;
+}
+
+int csfm_blob(const csfm_index* idx, const void** d_blob, uint64_t* bytes) {
+  if (!idx || !d_blob || !bytes) return fail(CSFM_ERR_INVALID, "null argument");
+  *d_blob = idx->d_blob;
+  *bytes = idx->blob_bytes;
+  return CSFM_OK;
+}
+
+int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownership, csfm_index** out) {
+  if (!out || !d_blob) return fail(CSFM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (bytes < kHeaderBytes) return fail(CSFM_ERR_FORMAT, "blob smaller than its header");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  BlobHeader h;
+  CSFM_CUDA(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost));
+  if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 1) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
+  if (h.total_bytes > bytes || h.levels == 0 || h.levels > kMaxLevels || h.nblk != h.n / kPayloadBits + 1 ||
+      h.off_levels < sizeof(BlobHeader) || h.off_ssa + h.nsamp * 4 > h.total_bytes || h.stride == 0 ||
+      h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * kLineBytes)
+    return fail(CSFM_ERR_FORMAT, "inconsistent blob header");
+  auto* idx = new (std::nothrow) csfm_index();
+  if (!idx) return fail(CSFM_ERR_NOMEM, "host allocation failed");
+  idx->device = device;
+  idx->d_blob = static_cast<uint8_t*>(d_blob);
+  idx->blob_bytes = h.total_bytes;
+  idx->owns_blob = take_ownership != 0;
+  idx->h = h;
+  rc = index_finish_handle(idx);
+  if (rc) {
+    idx->owns_blob = false;
+    csfm_destroy(idx);
+    return rc;
+  }
+  *out = idx;
+  return CSFM_OK;
+}
+
+int csfm_blob_to_host(const csfm_index* idx, void* out, uint64_t bytes) {
+  if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
+  if (bytes < idx->blob_bytes) return fail(CSFM_ERR_CAPACITY, "host buffer smaller than the blob");
+  DeviceGuard g(idx->device);
+  CSFM_CUDA(cudaMemcpy(out, idx->d_blob, idx->blob_bytes, cudaMemcpyDeviceToHost));
+  return CSFM_OK;
+}
+
+int csfm_from_host_blob(const void* blob, uint64_t bytes, int device, csfm_index** out) {
+  if (!out || !blob) return fail(CSFM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  if (bytes < kHeaderBytes) return fail(CSFM_ERR_FORMAT, "blob smaller than its header");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  void* d = nullptr;
+  CSFM_CUDA(cudaMalloc(&d, bytes));
+  cudaError_t e = cudaMemcpy(d, blob, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(CSFM_ERR_CUDA, cudaGetErrorString(e));
+  }
+  rc = csfm_attach_blob(d, bytes, device, 1, out);
+  if (rc) cudaFree(d);
+  return rc;
+}
+
+// ---- queries ----------------------------------------------------------------------------
+
+static void begin_call(csfm_index* idx) {
+  std::memset(&idx->stats, 0, sizeof idx->stats);
+  std::memset(idx->h_pinned, 0, 128);
+}
+
+static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
+  // caller has synchronised `stream`
+  const unsigned long long* hp = static_cast<const unsigned long long*>(idx->h_pinned);
+  if (idx->instr_mask & 1u) {
+    if (locate) idx->stats.lf_steps = hp[9]; else idx->stats.search_steps = hp[8];
+  }
+  if (idx->instr_mask & 2u) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->stats.kernel_ms = ms;
+  }
+  (void)stream;
+  return CSFM_OK;
+}
+
+int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
+                            uint64_t* d_counts, uint64_t* d_sp_ep, void* stream) {
+  if (!idx || (npat && (!d_offs || !d_counts))) return fail(CSFM_ERR_INVALID, "null argument");
+  DeviceGuard g(idx->device);
+  begin_call(idx);
+  return count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
+                     uint64_t* sp_ep) {
+  if (!idx || (npat && (!offs || !counts))) return fail(CSFM_ERR_INVALID, "null argument");
+  if (npat == 0) return CSFM_OK;
+  const uint64_t nbytes = offs[npat];
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  begin_call(idx);
+  cudaStream_t st = idx->stream;
+  // input staging: [offs (npat+1) u64][bytes]
+  const size_t offs_bytes = (npat + 1) * 8;
+  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 16);
+  if (rc) return rc;
+  const size_t out_bytes = npat * 8 * (sp_ep ? 3 : 1);
+  rc = idx->ws_out.ensure(out_bytes);
+  if (rc) return rc;
+  uint64_t* d_offs = idx->ws_in.as<uint64_t>();
+  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + offs_bytes;
+  uint64_t* d_counts = idx->ws_out.as<uint64_t>();
+  uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
+  CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, st));
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
+  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, st);
+  if (rc) return rc;
+  CSFM_CUDA(cudaMemcpyAsync(counts, d_counts, npat * 8, cudaMemcpyDeviceToHost, st));
+  if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, st));
+  CSFM_CUDA(cudaStreamSynchronize(st));
+  idx->stats.h2d_bytes = offs_bytes + nbytes;
+  idx->stats.d2h_bytes = out_bytes;
+  return end_call(idx, st, false);
+}
+
+int csfm_locate_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
+                             uint64_t limit, uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t cap,
+                             int32_t* d_status, uint64_t* total, void* stream) {
+  if (!idx || !total || !d_out_offs || (npat && !d_offs)) return fail(CSFM_ERR_INVALID, "null argument");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  begin_call(idx);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = locate_plan(idx, d_bytes, d_offs, npat, limit, d_out_offs, d_status, total, st);
+  if (rc) return rc;
+  if (d_out_pos == nullptr && cap == 0) return CSFM_OK;  // sizing call
+  if (cap < *total) return fail(CSFM_ERR_CAPACITY, "locate output buffer too small");
+  return locate_walk(idx, npat, d_out_offs, d_out_pos, *total, d_status, st);
+}
+
+int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t limit,
+                      uint64_t* out_offs, uint64_t* out_pos, uint64_t cap, int32_t* status, uint64_t* total) {
+  if (!idx || !total || !out_offs || (npat && !offs)) return fail(CSFM_ERR_INVALID, "null argument");
+  *total = 0;
+  if (npat == 0) {
+    out_offs[0] = 0;
+    return CSFM_OK;
+  }
+  const uint64_t nbytes = offs[npat];
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  begin_call(idx);
+  cudaStream_t st = idx->stream;
+  const size_t offs_bytes = (npat + 1) * 8;
+  const size_t status_bytes = (npat * 4 + 7) / 8 * 8;
+  // ws_in: [offs][bytes] ; ws_out: [out_offs (npat+1) u64][status npat i32] ; ws_pos: positions
+  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 16);
+  if (rc) return rc;
+  rc = idx->ws_out.ensure(offs_bytes + status_bytes);
+  if (rc) return rc;
+  uint64_t* d_offs = idx->ws_in.as<uint64_t>();
+  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + offs_bytes;
+  uint64_t* d_out_offs = idx->ws_out.as<uint64_t>();
+  int32_t* d_status = reinterpret_cast<int32_t*>(idx->ws_out.as<uint8_t>() + offs_bytes);
+  CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, st));
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
+  idx->stats.h2d_bytes = offs_bytes + nbytes;
+
+  uint64_t tot = 0;
+  rc = locate_plan(idx, d_bytes, d_offs, npat, limit, d_out_offs, d_status, &tot, st);
+  if (rc) return rc;
+  *total = tot;
+  CSFM_CUDA(cudaMemcpyAsync(out_offs, d_out_offs, offs_bytes, cudaMemcpyDeviceToHost, st));
+  idx->stats.d2h_bytes = offs_bytes;
+  const bool sizing = (out_pos == nullptr && cap == 0);
+  if (sizing || cap < tot) {
+    if (status) CSFM_CUDA(cudaMemcpyAsync(status, d_status, npat * 4, cudaMemcpyDeviceToHost, st));
+    CSFM_CUDA(cudaStreamSynchronize(st));
+    return sizing ? CSFM_OK : fail(CSFM_ERR_CAPACITY, "locate output buffer too small");
+  }
+  if (tot) {
+    rc = idx->ws_pos.ensure(tot * 8);
+    if (rc) return rc;
+    rc = locate_walk(idx, npat, d_out_offs, idx->ws_pos.as<uint64_t>(), tot, d_status, st);
+    if (rc) return rc;
+    CSFM_CUDA(cudaMemcpyAsync(out_pos, idx->ws_pos.p, tot * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (status) CSFM_CUDA(cudaMemcpyAsync(status, d_status, npat * 4, cudaMemcpyDeviceToHost, st));
+  CSFM_CUDA(cudaStreamSynchronize(st));
+  idx->stats.d2h_bytes += tot * 8 + (status ? npat * 4 : 0);
+  return end_call(idx, st, true);
+}
+
+int csfm_set_instrumentation(csfm_index* idx, uint32_t mask) {
+  if (!idx) return fail(CSFM_ERR_INVALID, "null argument");
+  idx->instr_mask = mask;
+  return CSFM_OK;
+}
+
+int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out) {
+  if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
+  // device-pointer calls are asynchronous: fold in whatever the instrumentation wrote so far
+  *out = idx->stats;
+  const unsigned long long* hp = static_cast<const unsigned long long*>(idx->h_pinned);
+  if (idx->instr_mask & 1u) {
+    if (!out->search_steps) out->search_steps = hp[8];
+    if (!out->lf_steps) out->lf_steps = hp[9];
+  }
+  if ((idx->instr_mask & 2u) && out->kernel_ms == 0.f) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) out->kernel_ms = ms;
+  }
+  return CSFM_OK;
+}
+
+int csfm_host_alloc(void** p, uint64_t bytes) {
+  if (!p) return fail(CSFM_ERR_INVALID, "null argument");
+  *p = nullptr;
+  cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? CSFM_ERR_NOMEM : CSFM_ERR_CUDA, cudaGetErrorString(e));
+  return CSFM_OK;
+}
+
+int csfm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+  return CSFM_OK;
+}
+
+}  // extern "C"

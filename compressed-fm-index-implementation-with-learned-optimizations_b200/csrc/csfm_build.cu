@@ -1,0 +1,335 @@
+// csfm_build.cu — BWT -> device-resident wavelet-matrix index (the "wm_build" kernels).
+//
+// Replaces cs::WaveletTree::build + cs::BitVector::build
+// (/root/reference/src/core/wavelet.cpp:14-53, src/core/bitvector.cpp:14-92) and the C-array
+// loop of FMIndex::build_from_text (src/api/fm_index.cpp:36-47). Same bit planes, different
+// container: 64-byte lines carrying their own absolute rank counter (csfm_common.cuh).
+//
+// Per level l (bit L-1-l of the compact symbol code):
+//   pack_level     one warp per 480-symbol line: 15 ballots -> 15 payload words + line popcount
+//   cub::ExclusiveSum over the line popcounts -> absolute rank before each line
+//   write_headers  word 0 of every line
+//   split_level    stable partition (zeros first, then ones) into the next level's order; the
+//                  destination of symbol i is exactly the rank formula the queries use:
+//                  bit ? zeros + rank1(i) : i - rank1(i)   (wavelet.cpp:47-51)
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "csfm_host.hpp"
+
+namespace csfm {
+
+namespace {
+
+__global__ void histogram_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                 unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 16;
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; base < n;
+       base += stride) {
+    if (base + 16 <= n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(data + base);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        atomicAdd(&sh[w[k] & 0xFF], 1u);
+        atomicAdd(&sh[(w[k] >> 8) & 0xFF], 1u);
+        atomicAdd(&sh[(w[k] >> 16) & 0xFF], 1u);
+        atomicAdd(&sh[w[k] >> 24], 1u);
+      }
+    } else {
+      for (uint64_t i = base; i < n; ++i) atomicAdd(&sh[data[i]], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+struct CodeTable {
+  uint8_t code[256];
+};
+
+__global__ void map_codes_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
+                                 uint64_t n, const __grid_constant__ CodeTable t) {
+  __shared__ uint8_t sc[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sc[i] = t.code[i];
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = sc[in[i]];
+}
+
+// One warp per line. Writes words 1..15 (payload) and 0 into word 0; line popcount to pop[].
+__global__ void pack_level_kernel(const uint8_t* __restrict__ cur, uint64_t n, int bit,
+                                  uint8_t* __restrict__ level, uint64_t nblk,
+                                  uint32_t* __restrict__ pop) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t b = warp; b < nblk; b += nwarps) {
+    const uint64_t i0 = b * kPayloadBits;
+    uint32_t mine = 0, total = 0;
+#pragma unroll
+    for (int t = 0; t < 15; ++t) {
+      const uint64_t i = i0 + 32 * t + lane;
+      const uint32_t v = (i < n) ? ((cur[i] >> bit) & 1u) : 0u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v);
+      if (lane == t + 1) mine = bal;  // lane k owns line word k
+      total += __popc(bal);
+    }
+    if (lane < 16) reinterpret_cast<uint32_t*>(level + b * kLineBytes)[lane] = mine;
+    if (lane == 0) pop[b] = total;
+  }
+}
+
+__global__ void write_headers_kernel(uint8_t* __restrict__ level, uint64_t nblk,
+                                     const uint32_t* __restrict__ rank_before) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += stride)
+    *reinterpret_cast<uint32_t*>(level + b * kLineBytes) = rank_before[b];
+}
+
+// Stable 0/1 split of the symbol sequence for the next level.
+__global__ void split_level_kernel(const uint8_t* __restrict__ cur, uint8_t* __restrict__ nxt,
+                                   uint64_t n, int bit, uint64_t nblk,
+                                   const uint32_t* __restrict__ rank_before, uint32_t zeros) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t b = warp; b < nblk; b += nwarps) {
+    const uint64_t i0 = b * kPayloadBits;
+    uint32_t r = rank_before[b];
+#pragma unroll
+    for (int t = 0; t < 15; ++t) {
+      const uint64_t i = i0 + 32 * t + lane;
+      const bool valid = i < n;
+      const uint8_t sym = valid ? cur[i] : 0;
+      const uint32_t v = valid ? ((sym >> bit) & 1u) : 0u;
+      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, v);
+      const uint32_t r1 = r + __popc(bal & lt);  // rank1(i)
+      if (valid) {
+        const uint64_t dst = v ? (uint64_t)zeros + r1 : i - r1;
+        nxt[dst] = sym;
+      }
+      r += __popc(bal);
+    }
+  }
+}
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+uint32_t bit_reverse(uint32_t v, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+
+}  // namespace
+
+// Host-side derivation of every table from the byte histogram.
+static void fill_tables(BlobHeader& h, const unsigned long long hist[256], uint32_t flags) {
+  uint32_t cum = 0;
+  for (int c = 0; c < 256; ++c) {  // fm_index.cpp:41-46
+    h.C[c] = cum;
+    cum += (uint32_t)hist[c];
+  }
+  h.C[256] = cum;
+  uint32_t sigma = 0;
+  std::memset(h.code_of_byte, 0, 256);
+  std::memset(h.byte_of_code, 0, 256);
+  const bool compact = !(flags & CSFM_BUILD_NO_COMPACT);
+  for (int c = 0; c < 256; ++c) {
+    if (hist[c]) {
+      if (compact) {
+        h.code_of_byte[c] = (uint8_t)sigma;
+        h.byte_of_code[sigma] = (uint8_t)c;
+      }
+      ++sigma;
+    }
+  }
+  h.sigma = sigma;
+  uint32_t L = 8;
+  if (compact) {
+    L = 1;
+    while ((1u << L) < sigma) ++L;
+  } else {
+    for (int c = 0; c < 256; ++c) {
+      h.code_of_byte[c] = (uint8_t)c;
+      h.byte_of_code[c] = (uint8_t)c;
+    }
+  }
+  h.levels = L;
+  // path(code,0) = number of symbols whose L-bit-reversed code is smaller: after L stable
+  // 0/1 splits the sequence is ordered by the bit-reversed code (last split most significant).
+  const uint32_t ncodes = 1u << L;
+  std::vector<uint64_t> freq_by_rev(ncodes, 0);
+  std::vector<uint32_t> code_freq(ncodes, 0);
+  for (int c = 0; c < 256; ++c)
+    if (hist[c]) code_freq[h.code_of_byte[c]] += (uint32_t)hist[c];
+  for (uint32_t code = 0; code < ncodes; ++code) freq_by_rev[bit_reverse(code, L)] = code_freq[code];
+  std::vector<uint32_t> start_by_rev(ncodes, 0);
+  uint32_t acc = 0;
+  for (uint32_t r = 0; r < ncodes; ++r) {
+    start_by_rev[r] = acc;
+    acc += (uint32_t)freq_by_rev[r];
+  }
+  std::memset(h.base_by_byte, 0, sizeof h.base_by_byte);
+  std::memset(h.base_by_code, 0, sizeof h.base_by_code);
+  for (int c = 0; c < 256; ++c) {
+    if (!hist[c]) continue;
+    const uint32_t code = h.code_of_byte[c];
+    const uint32_t node_start = start_by_rev[bit_reverse(code, L)];
+    h.base_by_byte[c] = h.C[c] - node_start;  // u32 wrap-around is intended
+    h.base_by_code[code] = h.C[c] - node_start;
+  }
+}
+
+int index_finish_handle(csfm_index* idx) {
+  cudaDeviceProp prop;
+  CSFM_CUDA(cudaGetDeviceProperties(&prop, idx->device));
+  idx->num_sms = prop.multiProcessorCount;
+  const BlobHeader& h = idx->h;
+  IndexView& v = idx->view;
+  v.levels = idx->d_blob + h.off_levels;
+  v.ssa = reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_ssa);
+  v.hdr = reinterpret_cast<const BlobHeader*>(idx->d_blob);
+  v.level_stride = h.level_stride;
+  v.n = (uint32_t)h.n;
+  v.L = h.levels;
+  v.stride = h.stride;
+  v.nsamp = (uint32_t)h.nsamp;
+  for (int l = 0; l < (int)kMaxLevels; ++l) v.zeros[l] = h.zeros[l];
+  if (!idx->stream) CSFM_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+  if (!idx->ev0) CSFM_CUDA(cudaEventCreate(&idx->ev0));
+  if (!idx->ev1) CSFM_CUDA(cudaEventCreate(&idx->ev1));
+  if (!idx->d_counters) {
+    CSFM_CUDA(cudaMalloc(&idx->d_counters, kCounterSlots * 4 * sizeof(unsigned long long)));
+    CSFM_CUDA(cudaMemset(idx->d_counters, 0, kCounterSlots * 4 * sizeof(unsigned long long)));
+  }
+  if (!idx->h_pinned) CSFM_CUDA(cudaHostAlloc(&idx->h_pinned, 4096, cudaHostAllocDefault));
+  return CSFM_OK;
+}
+
+int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ssa, uint64_t nsamp,
+                          uint32_t stride, int device, uint32_t flags, csfm_index** out) {
+  if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
+  if (stride == 0) return fail(CSFM_ERR_INVALID, "ssa_stride must be > 0");
+  cudaStream_t st = nullptr;  // construction runs on the legacy default stream of the device
+
+  // 1) byte histogram -> C, compact codes, level count, per-symbol base
+  unsigned long long* d_hist = nullptr;
+  CSFM_CUDA(cudaMalloc(&d_hist, 256 * sizeof(unsigned long long)));
+  CSFM_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), st));
+  if (n) histogram_kernel<<<1024, 256, 0, st>>>(d_bwt, n, d_hist);
+  unsigned long long hist[256];
+  CSFM_CUDA(cudaMemcpy(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost));
+  cudaFree(d_hist);
+
+  auto* idx = new csfm_index();
+  idx->device = device;
+  BlobHeader& h = idx->h;
+  std::memset(&h, 0, sizeof h);
+  std::memcpy(h.magic, "CSFMDEV1", 8);
+  h.version = 1;
+  h.n = n;
+  h.stride = stride;
+  h.nsamp = nsamp;
+  fill_tables(h, hist, flags);
+  const uint32_t L = h.levels;
+  h.nblk = n / kPayloadBits + 1;
+  h.off_levels = kHeaderBytes;
+  h.level_stride = align_up(h.nblk * kLineBytes, 256);
+  h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
+  h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
+
+  idx->blob_bytes = h.total_bytes;
+  idx->owns_blob = true;
+  cudaError_t e = cudaMalloc(&idx->d_blob, idx->blob_bytes);
+  if (e != cudaSuccess) {
+    delete idx;
+    return fail(CSFM_ERR_NOMEM, std::string("cudaMalloc(index blob): ") + cudaGetErrorString(e));
+  }
+
+  // 2) levels
+  uint8_t *d_cur = nullptr, *d_nxt = nullptr;
+  uint32_t *d_pop = nullptr, *d_rank = nullptr;
+  void* d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_cur); cudaFree(d_nxt); cudaFree(d_pop); cudaFree(d_rank); cudaFree(d_scan_tmp);
+  };
+  auto bail = [&](int code, const std::string& m) {
+    cleanup();
+    csfm_destroy(idx);
+    return fail(code, m);
+  };
+#define BUILD_CUDA(expr)                                                         \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess)                                                       \
+      return bail(_e == cudaErrorMemoryAllocation ? CSFM_ERR_NOMEM : CSFM_ERR_CUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+  const uint64_t nbuf = n ? n : 1;
+  BUILD_CUDA(cudaMalloc(&d_cur, nbuf));
+  BUILD_CUDA(cudaMalloc(&d_nxt, nbuf));
+  BUILD_CUDA(cudaMalloc(&d_pop, h.nblk * 4));
+  BUILD_CUDA(cudaMalloc(&d_rank, h.nblk * 4));
+  BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, d_pop, d_rank, (int64_t)h.nblk, st));
+  BUILD_CUDA(cudaMalloc(&d_scan_tmp, scan_tmp_bytes ? scan_tmp_bytes : 16));
+
+  if (n) {
+    CodeTable ct;
+    std::memcpy(ct.code, h.code_of_byte, 256);
+    map_codes_kernel<<<2048, 256, 0, st>>>(d_bwt, d_cur, n, ct);
+  }
+  const int wpb = 8;  // warps per block
+  const uint64_t want_blocks = (h.nblk + wpb - 1) / wpb;
+  const int grid = (int)std::min<uint64_t>(want_blocks, 148ull * 64);
+  for (uint32_t l = 0; l < L; ++l) {
+    const int bit = (int)(L - 1 - l);
+    uint8_t* level = idx->d_blob + h.off_levels + (uint64_t)l * h.level_stride;
+    pack_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, bit, level, h.nblk, d_pop);
+    BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop, d_rank, (int64_t)h.nblk, st));
+    write_headers_kernel<<<1024, 256, 0, st>>>(level, h.nblk, d_rank);
+    uint32_t last_rank = 0, last_pop = 0;
+    BUILD_CUDA(cudaMemcpyAsync(&last_rank, d_rank + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
+    BUILD_CUDA(cudaMemcpyAsync(&last_pop, d_pop + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
+    BUILD_CUDA(cudaStreamSynchronize(st));
+    const uint32_t ones = last_rank + last_pop;
+    h.zeros[l] = (uint32_t)n - ones;
+    if (l + 1 < L && n) {
+      split_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, d_nxt, n, bit, h.nblk, d_rank, h.zeros[l]);
+      std::swap(d_cur, d_nxt);
+    }
+  }
+  // 3) SA samples + header
+  if (nsamp)
+    BUILD_CUDA(cudaMemcpyAsync(idx->d_blob + h.off_ssa, d_ssa, nsamp * 4, cudaMemcpyDeviceToDevice, st));
+  {
+    std::vector<uint8_t> hdr(kHeaderBytes, 0);
+    std::memcpy(hdr.data(), &h, sizeof h);
+    BUILD_CUDA(cudaMemcpyAsync(idx->d_blob, hdr.data(), kHeaderBytes, cudaMemcpyHostToDevice, st));
+    BUILD_CUDA(cudaStreamSynchronize(st));
+  }
+  BUILD_CUDA(cudaGetLastError());
+  cleanup();
+#undef BUILD_CUDA
+  int rc = index_finish_handle(idx);
+  if (rc != CSFM_OK) {
+    csfm_destroy(idx);
+    return rc;
+  }
+  *out = idx;
+  return CSFM_OK;
+}
+
+}  // namespace csfm

@@ -1,0 +1,91 @@
+// csfm_host.hpp — host-side handle and helpers shared by the library's translation units.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/csfm.h"
+#include "csfm_common.cuh"
+
+namespace csfm {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define CSFM_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      return ::csfm::fail(_e == cudaErrorMemoryAllocation ? CSFM_ERR_NOMEM : CSFM_ERR_CUDA, \
+                          std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    }                                                                                       \
+  } while (0)
+
+// Grow-only device buffer (workspace reuse across batch calls).
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes);  // returns csfm_status
+  void release();
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev);
+  ~DeviceGuard();
+};
+
+}  // namespace csfm
+
+struct csfm_index {
+  int device = 0;
+  int num_sms = 0;
+  uint8_t* d_blob = nullptr;
+  uint64_t blob_bytes = 0;
+  bool owns_blob = true;
+  csfm::BlobHeader h{};  // host copy of the header
+  csfm::IndexView view{};
+  uint32_t* d_sa = nullptr;  // CSFM_BUILD_KEEP_SA
+
+  cudaStream_t stream = nullptr;  // used by the host-pointer API
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
+  unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators
+  uint32_t counter_slot = 0;
+  void* h_pinned = nullptr;  // small pinned scratch (totals, stats)
+
+  uint32_t instr_mask = 0;
+  csfm_call_stats stats{};
+  std::mutex mu;
+};
+
+namespace csfm {
+
+constexpr uint32_t kCounterSlots = 256;  // each slot = 4 x u64
+
+// csfm_build.cu
+int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ssa, uint64_t nsamp,
+                          uint32_t stride, int device, uint32_t flags, csfm_index** out);
+int index_finish_handle(csfm_index* idx);  // fills view/stream/workspace after d_blob + h are set
+// csfm_sa.cu
+int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
+                        uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,
+                        uint32_t** d_sa_out /*nullable: keep SA*/);
+// csfm_query.cu
+int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
+                 uint64_t* d_counts, uint64_t* d_sp_ep, uint32_t* d_row_sp, uint32_t* d_row_cnt,
+                 uint64_t limit, cudaStream_t stream);
+int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
+                uint64_t limit, uint64_t* d_out_offs, int32_t* d_status, uint64_t* total,
+                cudaStream_t stream);
+int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos,
+                uint64_t total, int32_t* d_status, cudaStream_t stream);
+int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream);
+unsigned long long* next_counter_slot(csfm_index* idx);
+
+}  // namespace csfm

@@ -1,0 +1,506 @@
+// csfm_query.cu — backward-search (count), LF-walk (locate) and access kernels for sm_100a.
+//
+// Replaces cs::FMIndex::count / locate (/root/reference/src/api/fm_index.cpp:79-157),
+// cs::WaveletTree::rank / access (src/core/wavelet.cpp:59-128) and cs::BitVector::rank1
+// (src/core/bitvector.cpp:165-230) on the query path.
+//
+// Execution model (all three kernels): a sub-warp of 4 lanes owns one query / occurrence /
+// position. One rank = one 64-byte line = four coalesced 128-bit loads (one per lane), masked
+// popc, two xor-shuffles. The 8 sub-warps of a warp run ONE flat state machine in lock-step —
+// each loop trip is "one wavelet level for whatever query my sub-warp currently holds" — so
+// queries of different length never diverge the instruction stream, and a sub-warp that
+// finishes refills from a warp-local chunk of the batch cursor (ballot-ranked, one global
+// atomic per 32 queries). Grids are persistent: SM count x resident CTAs.
+#include <algorithm>
+#include <cstring>
+
+#include <cub/device/device_scan.cuh>
+
+#include "csfm_host.hpp"
+
+namespace csfm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kChunk = 32;  // queries fetched per warp per global atomic
+
+struct Tables {  // per-CTA shared-memory copy of the byte-indexed tables
+  uint32_t C[257];
+  uint32_t pad[3];
+  uint32_t base_by_byte[256];
+  uint32_t base_by_code[256];
+  uint8_t code_of_byte[256];
+  uint8_t byte_of_code[256];
+};
+
+__device__ __forceinline__ void load_tables(Tables& t, const BlobHeader* __restrict__ h) {
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) t.C[i] = h->C[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    t.base_by_byte[i] = h->base_by_byte[i];
+    t.base_by_code[i] = h->base_by_code[i];
+    t.code_of_byte[i] = h->code_of_byte[i];
+    t.byte_of_code[i] = h->byte_of_code[i];
+  }
+  __syncthreads();
+}
+
+// Warp-local work queue over [0,total): returns this sub-warp's next item or ~0ull.
+struct WarpQueue {
+  unsigned long long next = 0, end = 0;
+  bool exhausted = false;
+};
+
+// Called by all 32 lanes (converged). `need` = this sub-warp wants an item. Returns the item
+// index or ~0ull. A partially served round simply leaves some sub-warps idle for one trip.
+__device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need, int lane,
+                                                         unsigned long long* cursor,
+                                                         unsigned long long total) {
+  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & 0x11111111u;  // leaders
+  if (need_mask == 0) return ~0ull;
+  if (q.next >= q.end && !q.exhausted) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) {
+      q.exhausted = true;
+    } else {
+      q.next = base;
+      q.end = (base + kChunk < total) ? base + kChunk : total;
+    }
+  }
+  const unsigned long long avail = q.end - q.next;
+  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
+  const unsigned cnt = __popc(need_mask);
+  unsigned long long item = ~0ull;
+  if (need && my_rank < avail) item = q.next + my_rank;
+  q.next += (cnt < avail) ? cnt : avail;
+  return item;
+}
+
+// ------------------------------------------------------------------------------------------
+// count: backward search (fm_index.cpp:79-101)
+// ------------------------------------------------------------------------------------------
+struct CountArgs {
+  const uint8_t* bytes;
+  const uint64_t* offs;
+  unsigned long long npat;
+  uint64_t* counts;    // nullable
+  uint64_t* sp_ep;     // nullable, 2 per query
+  uint32_t* row_sp;    // nullable (locate pass 1)
+  uint32_t* row_cnt;   // nullable (locate pass 1): min(count, limit), 0 for empty patterns
+  uint32_t limit32;
+  unsigned long long* cursor;
+  unsigned long long* steps_total;  // nullable (instrumentation)
+};
+
+__global__ void __launch_bounds__(kThreads, 6)
+count_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const uint32_t L = iv.L;
+  WarpQueue wq;
+
+  bool active = false;
+  unsigned long long q = 0;       // query index
+  const uint8_t* ptr = nullptr;   // address of the character being processed
+  uint32_t rem = 0;               // characters left including the current one
+  uint32_t sp_pos = 0, ep_pos = 0, base = 0, code = 0, level = 0, next_byte = 0;
+  uint32_t my_steps = 0;
+
+  auto finish = [&](uint32_t cnt, uint32_t sp, uint32_t ep) {
+    if (j == 0) {
+      if (a.counts) a.counts[q] = cnt;
+      if (a.sp_ep) {
+        a.sp_ep[2 * q] = sp;
+        a.sp_ep[2 * q + 1] = ep;
+      }
+      if (a.row_sp) {
+        a.row_sp[q] = sp;
+        a.row_cnt[q] = cnt < a.limit32 ? cnt : a.limit32;
+      }
+    }
+    active = false;
+  };
+  // Begin the step for byte `b` on interval [sp,ep): sets the per-step constants.
+  auto begin_step = [&](uint32_t b, uint32_t sp, uint32_t ep) {
+    ++my_steps;
+    if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
+      finish(0, 0, 0);
+      return;
+    }
+    code = tb.code_of_byte[b];
+    base = tb.base_by_byte[b];
+    sp_pos = sp;
+    ep_pos = ep;
+    level = 0;
+    if (rem > 1) next_byte = ptr[-1];  // prefetch: in flight during the L rank levels
+  };
+
+  for (;;) {
+    // ---- refill -----------------------------------------------------------------------
+    const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.npat);
+    if (item != ~0ull) {
+      q = item;
+      const uint64_t o0 = a.offs[q], o1 = a.offs[q + 1];
+      const uint64_t m = o1 - o0;
+      active = true;
+      if (m == 0) {
+        // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
+        if (j == 0) {
+          if (a.counts) a.counts[q] = iv.n;
+          if (a.sp_ep) { a.sp_ep[2 * q] = 0; a.sp_ep[2 * q + 1] = 0; }
+          if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
+        }
+        active = false;
+      } else {
+        // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
+        const uint32_t b = a.bytes[o1 - 1];
+        const uint32_t sp = tb.C[b], ep = tb.C[b + 1];
+        ++my_steps;
+        if (sp >= ep) {
+          finish(0, 0, 0);
+        } else if (m == 1) {
+          finish(ep - sp, sp, ep);
+        } else {
+          rem = (uint32_t)(m - 1);
+          ptr = a.bytes + (o1 - 2);
+          begin_step(*ptr, sp, ep);
+        }
+      }
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+
+    // ---- one wavelet level for the two interval ends ------------------------------------
+    uint4 ws = make_uint4(0, 0, 0, 0), we = ws;
+    uint32_t os = 0, oe = 0;
+    if (active) {
+      const uint8_t* lv = iv.levels + (uint64_t)level * iv.level_stride + j * 16;
+      const uint32_t bs = sp_pos / kPayloadBits, be = ep_pos / kPayloadBits;
+      os = sp_pos - bs * kPayloadBits;
+      oe = ep_pos - be * kPayloadBits;
+      ws = ldg_nc_v4(lv + (uint64_t)bs * kLineBytes);
+      we = (be == bs) ? ws : ldg_nc_v4(lv + (uint64_t)be * kLineBytes);
+    }
+    const uint32_t rs = group4_sum(lane_partial_rank(ws, os, j));
+    const uint32_t re = group4_sum(lane_partial_rank(we, oe, j));
+    if (active) {
+      const uint32_t bit = (code >> (L - 1 - level)) & 1u;
+      const uint32_t z = iv.zeros[level];
+      sp_pos = bit ? z + rs : sp_pos - rs;  // wavelet.cpp:73-87 for the `end` position
+      ep_pos = bit ? z + re : ep_pos - re;
+      ++level;
+      if (level == L) {
+        const uint32_t sp = base + sp_pos, ep = base + ep_pos;  // fm_index.cpp:92-93
+        if (sp >= ep) {
+          finish(0, 0, 0);
+        } else if (--rem == 0) {
+          finish(ep - sp, sp, ep);
+        } else {
+          --ptr;
+          begin_step(next_byte, sp, ep);
+        }
+      }
+    }
+  }
+  if (a.steps_total) {
+    unsigned s = (j == 0) ? my_steps : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// locate: rows -> text positions (fm_index.cpp:125-153, LF of fm_index.hpp:62-66)
+// ------------------------------------------------------------------------------------------
+// out_pos[out_offs[q] + k] = sp[q] + k  (SA rows of query q, in row order)
+__global__ void expand_rows_kernel(const uint32_t* __restrict__ row_sp,
+                                   const uint64_t* __restrict__ out_offs, uint64_t npat,
+                                   uint64_t* __restrict__ out_pos) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t q = warp; q < npat; q += nwarps) {
+    const uint64_t o0 = out_offs[q], o1 = out_offs[q + 1];
+    const uint64_t sp = row_sp[q];
+    for (uint64_t k = lane; k < o1 - o0; k += 32) out_pos[o0 + k] = sp + k;
+  }
+}
+
+struct WalkArgs {
+  uint64_t* out_pos;  // in: SA row, out: text position
+  unsigned long long total;
+  const uint64_t* out_offs;  // npat+1 (to attribute a failed walk to its query)
+  unsigned long long npat;
+  int32_t* status;
+  unsigned long long* cursor;
+  unsigned long long* lf_total;  // nullable
+};
+
+__global__ void __launch_bounds__(kThreads, 6)
+walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const uint32_t L = iv.L;
+  WarpQueue wq;
+
+  bool active = false;
+  unsigned long long slot = 0;
+  uint32_t start = 0, p = 0, steps = 0, code = 0, level = 0;
+  uint32_t my_lf = 0;
+
+  // Where the reference throws, the whole query fails: attribute the slot to its query.
+  auto fail_walk = [&](int why) {
+    if (j == 0) {
+      unsigned long long lo = 0, hi = a.npat;  // last q with out_offs[q] <= slot
+      while (hi - lo > 1) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (a.out_offs[mid] <= slot) lo = mid; else hi = mid;
+      }
+      if (a.status) atomicMax(&a.status[lo], why);
+      a.out_pos[slot] = 0;
+    }
+    active = false;
+  };
+  auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]
+    const uint32_t k = row / iv.stride;
+    if (k >= iv.nsamp) {  // fm_index.cpp:141-146 (unreachable for a consistent index)
+      fail_walk((int)CSFM_Q_SSA_OOB);
+      return;
+    }
+    if (j == 0) {
+      uint64_t pos = (uint64_t)iv.ssa[k] + steps;  // fm_index.cpp:147-152
+      if (pos >= iv.n) pos -= iv.n;                // sa_val < n and steps < n
+      a.out_pos[slot] = pos;
+    }
+    active = false;
+  };
+
+  for (;;) {
+    const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
+    if (item != ~0ull) {
+      slot = item;
+      start = (uint32_t)a.out_pos[slot];
+      steps = 0;
+      active = true;
+      if (start % iv.stride == 0) {
+        emit(start);
+      } else {
+        p = start;
+        code = 0;
+        level = 0;
+      }
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+
+    // one level of access(p) fused with rank: both follow the same line (wavelet.cpp:102-128)
+    uint4 w = make_uint4(0, 0, 0, 0);
+    uint32_t off = 0;
+    if (active) {
+      const uint32_t blk = p / kPayloadBits;
+      off = p - blk * kPayloadBits;
+      w = ldg_nc_v4(iv.levels + (uint64_t)level * iv.level_stride + (uint64_t)blk * kLineBytes + j * 16);
+    }
+    const uint32_t r = group4_sum(lane_partial_rank(w, off, j));
+    const uint32_t kw = 1 + (off >> 5);  // line word holding bit `off`
+    const uint32_t comp = kw & 3;
+    const uint32_t mine = comp == 0 ? w.x : comp == 1 ? w.y : comp == 2 ? w.z : w.w;
+    const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, mine, (lane & ~3) | (kw >> 2));
+    if (active) {
+      const uint32_t bit = (wsel >> (off & 31)) & 1u;
+      p = bit ? iv.zeros[level] + r : p - r;
+      code = (code << 1) | bit;
+      ++level;
+      if (level == L) {
+        // p = path(c,i); LF(i) = C[c] + rank(c,i) = base[c] + path(c,i)  (fm_index.hpp:62-66)
+        const uint32_t row = tb.base_by_code[code] + p;
+        ++steps;
+        ++my_lf;
+        if (row % iv.stride == 0) {
+          emit(row);
+        } else if (row == start || steps >= iv.n) {
+          // LF is a permutation: back at the start without meeting a sampled row means the
+          // reference would walk n steps and throw (fm_index.cpp:130-138).
+          fail_walk((int)CSFM_Q_LF_WALK_EXCEEDED);
+        } else {
+          p = row;
+          code = 0;
+          level = 0;
+        }
+      }
+    }
+  }
+  if (a.lf_total) {
+    unsigned s = (j == 0) ? my_lf : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0 && s) atomicAdd(a.lf_total, (unsigned long long)s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// access: BWT[i] for all i (wavelet.cpp:102-128) — verification / export, not a query path
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+access_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const uint64_t group = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+  const uint64_t trips = ((uint64_t)iv.n + ngroups - 1) / ngroups;
+  for (uint64_t t = 0; t < trips; ++t) {
+    const uint64_t i = t * ngroups + group;
+    const bool valid = i < iv.n;
+    uint32_t p = valid ? (uint32_t)i : 0, code = 0;
+    for (uint32_t level = 0; level < iv.L; ++level) {
+      const uint32_t blk = p / kPayloadBits, off = p - blk * kPayloadBits;
+      const uint4 w = ldg_nc_v4(iv.levels + (uint64_t)level * iv.level_stride +
+                                (uint64_t)blk * kLineBytes + j * 16);
+      const uint32_t r = group4_sum(lane_partial_rank(w, off, j));
+      const uint32_t kw = 1 + (off >> 5), comp = kw & 3;
+      const uint32_t mine = comp == 0 ? w.x : comp == 1 ? w.y : comp == 2 ? w.z : w.w;
+      const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, mine, (lane & ~3) | (kw >> 2));
+      const uint32_t bit = (wsel >> (off & 31)) & 1u;
+      p = bit ? iv.zeros[level] + r : p - r;
+      code = (code << 1) | bit;
+    }
+    if (valid && j == 0) out[i] = tb.byte_of_code[code];
+  }
+}
+
+int persistent_grid(const csfm_index* idx, const void* kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return idx->num_sms * per_sm;
+}
+
+}  // namespace
+
+unsigned long long* next_counter_slot(csfm_index* idx) {
+  const uint32_t s = idx->counter_slot++ % kCounterSlots;
+  return idx->d_counters + (size_t)s * 4;
+}
+
+int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
+                 uint64_t* d_counts, uint64_t* d_sp_ep, uint32_t* d_row_sp, uint32_t* d_row_cnt,
+                 uint64_t limit, cudaStream_t stream) {
+  if (npat == 0) return CSFM_OK;
+  unsigned long long* ctr = next_counter_slot(idx);
+  CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
+  CountArgs a{};
+  a.bytes = d_bytes;
+  a.offs = d_offs;
+  a.npat = npat;
+  a.counts = d_counts;
+  a.sp_ep = d_sp_ep;
+  a.row_sp = d_row_sp;
+  a.row_cnt = d_row_cnt;
+  a.limit32 = limit > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)limit;
+  a.cursor = ctr;
+  a.steps_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
+  const int grid_max = persistent_grid(idx, (const void*)count_kernel);
+  const uint64_t want = (npat * 4 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
+  const bool timed = (idx->instr_mask & 2u) != 0;
+  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
+  count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
+  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
+  CSFM_CUDA(cudaGetLastError());
+  idx->stats.kernel_launches += 1;
+  if (a.steps_total)
+    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 8, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
+  return CSFM_OK;
+}
+
+// Pass 1+2 of locate: intervals, then out_offs = exclusive prefix of min(count, limit).
+// Synchronises `stream` (the total decides the size of the position buffer).
+int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat, uint64_t limit,
+                uint64_t* d_out_offs, int32_t* d_status, uint64_t* total, cudaStream_t stream) {
+  *total = 0;
+  if (npat == 0) {
+    CSFM_CUDA(cudaMemsetAsync(d_out_offs, 0, 8, stream));
+    CSFM_CUDA(cudaStreamSynchronize(stream));
+    return CSFM_OK;
+  }
+  int rc = idx->ws_tmp.ensure(npat * 8 + 256);
+  if (rc) return rc;
+  uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
+  uint32_t* d_row_cnt = d_row_sp + npat;
+  const uint32_t saved_mask = idx->instr_mask;
+  idx->instr_mask &= ~3u;  // in locate the instrumentation belongs to the walk kernel
+  rc = count_device(idx, d_bytes, d_offs, npat, nullptr, nullptr, d_row_sp, d_row_cnt, limit, stream);
+  idx->instr_mask = saved_mask;
+  if (rc) return rc;
+  // u32 inputs accumulated into u64 outputs (the init value's type drives the accumulator)
+  size_t tmp_bytes = 0;
+  CSFM_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, d_row_cnt, d_out_offs, cub::Sum(), (uint64_t)0,
+                                           (int64_t)npat, stream));
+  rc = idx->ws_scan.ensure(tmp_bytes + 16);
+  if (rc) return rc;
+  CSFM_CUDA(cub::DeviceScan::ExclusiveScan(idx->ws_scan.p, tmp_bytes, d_row_cnt, d_out_offs, cub::Sum(), (uint64_t)0,
+                                           (int64_t)npat, stream));
+  idx->stats.kernel_launches += 2;  // cub scan: init + scan kernels
+  uint64_t* h = reinterpret_cast<uint64_t*>(idx->h_pinned);
+  h[0] = h[1] = 0;
+  CSFM_CUDA(cudaMemcpyAsync(&h[0], d_out_offs + (npat - 1), 8, cudaMemcpyDeviceToHost, stream));
+  CSFM_CUDA(cudaMemcpyAsync(&h[1], d_row_cnt + (npat - 1), 4, cudaMemcpyDeviceToHost, stream));
+  CSFM_CUDA(cudaStreamSynchronize(stream));
+  const uint64_t tot = h[0] + (uint32_t)h[1];
+  *total = tot;
+  h[2] = tot;
+  CSFM_CUDA(cudaMemcpyAsync(d_out_offs + npat, &h[2], 8, cudaMemcpyHostToDevice, stream));
+  if (d_status) CSFM_CUDA(cudaMemsetAsync(d_status, 0, npat * 4, stream));
+  return CSFM_OK;
+}
+
+// Pass 3+4 of locate: SA rows of every slot, then the LF walks. Asynchronous on `stream`.
+// Uses the intervals left in idx->ws_tmp by locate_plan.
+int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
+                int32_t* d_status, cudaStream_t stream) {
+  if (npat == 0 || total == 0) return CSFM_OK;
+  const uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
+  expand_rows_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(d_row_sp, d_out_offs, npat, d_out_pos);
+  unsigned long long* ctr = next_counter_slot(idx);
+  CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
+  WalkArgs w{};
+  w.out_pos = d_out_pos;
+  w.total = total;
+  w.out_offs = d_out_offs;
+  w.npat = npat;
+  w.status = d_status;
+  w.cursor = ctr;
+  w.lf_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
+  const int grid_max = persistent_grid(idx, (const void*)walk_kernel);
+  const uint64_t want = (total * 4 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
+  const bool timed = (idx->instr_mask & 2u) != 0;
+  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
+  walk_kernel<<<grid, kThreads, 0, stream>>>(idx->view, w);
+  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
+  CSFM_CUDA(cudaGetLastError());
+  idx->stats.kernel_launches += 2;
+  if (w.lf_total)
+    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 9, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
+  return CSFM_OK;
+}
+
+int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream) {
+  if (idx->h.n == 0) return CSFM_OK;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, access_kernel, kThreads, 0);
+  if (per_sm < 1) per_sm = 1;
+  const uint64_t want = (idx->h.n * 4 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<uint64_t>(want, (uint64_t)idx->num_sms * per_sm);
+  access_kernel<<<grid, kThreads, 0, stream>>>(idx->view, d_out);
+  CSFM_CUDA(cudaGetLastError());
+  return CSFM_OK;
+}
+
+}  // namespace csfm

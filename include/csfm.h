@@ -1,0 +1,175 @@
+/* include/csfm.h — C ABI of the B200-native FM-index query engine (libcsfm.so).
+ *
+ * This is the drop-in boundary for the reference's hot path. The reference has no FFI layer:
+ * its boundary is the C++ class cs::FMIndex (/root/reference/src/api/fm_index.hpp:9-68). Each
+ * entry point below names the reference interface it replaces; the C++ class that mirrors
+ * cs::FMIndex on top of this ABI lives in
+ * compressed-fm-index-implementation-with-learned-optimizations_b200/host/src/api/fm_index.hpp.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; nothing throws across the boundary: every function returns
+ *    a csfm_status (0 = ok) and csfm_last_error() gives the message for the calling thread;
+ *  - "host" functions take host pointers (pageable or pinned; pinned buffers from
+ *    csfm_host_alloc avoid a staging copy) and return when the results are in the out buffers;
+ *  - "_device" functions take device pointers on the index's device and a cudaStream_t passed
+ *    as void*; they only enqueue work (results are ready when the stream reaches that point),
+ *    except where a host-visible total is returned (documented per function);
+ *  - patterns travel packed: `bytes` holds all pattern bytes back to back, `offs[npat+1]`
+ *    (uint64) the start of each pattern, offs[npat] = total bytes. Patterns are borrowed;
+ *  - all results are bit-exact with the reference on the same text and patterns, including its
+ *    quirks: count("") == n, cyclic over-count without a terminator, locate
+ *    positions in SA-row order, an error status where the reference throws;
+ *  - n must be < 2^32 - 1, as in the reference (uint32 SA / C array, fm_index.hpp:43-44);
+ *  - there is no CPU fallback: without a usable CUDA device every call fails with
+ *    CSFM_ERR_CUDA.
+ */
+#ifndef CSFM_H
+#define CSFM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CSFM_API __attribute__((visibility("default")))
+#else
+#define CSFM_API
+#endif
+
+typedef struct csfm_index csfm_index; /* opaque; one handle <-> one device */
+
+/* Library status codes. */
+typedef enum {
+  CSFM_OK = 0,
+  CSFM_ERR_INVALID = 1,   /* bad argument */
+  CSFM_ERR_CUDA = 2,      /* CUDA runtime / driver error, or no device */
+  CSFM_ERR_NOMEM = 3,     /* host or device allocation failed */
+  CSFM_ERR_TOO_LARGE = 4, /* n >= 2^32 - 1 */
+  CSFM_ERR_CAPACITY = 5,  /* locate output buffer too small; *total tells the need */
+  CSFM_ERR_FORMAT = 6     /* malformed index blob */
+} csfm_status;
+
+/* Per-query status of locate (where cs::FMIndex::locate throws, fm_index.cpp:136-146). */
+typedef enum {
+  CSFM_Q_OK = 0,
+  CSFM_Q_LF_WALK_EXCEEDED = 1, /* "locate: LF walk exceeded text length" (fm_index.cpp:136-138) */
+  CSFM_Q_SSA_OOB = 2           /* "locate: SSA sample index out of range" (fm_index.cpp:141-146) */
+} csfm_query_status;
+
+/* Mirrors cs::BuildParams (fm_index.hpp:11-14) field for field. As in the reference, only
+ * ssa_stride is honoured (fm_index.cpp:58); S, s and eps are accepted and ignored. */
+typedef struct {
+  uint32_t S, s, ssa_stride;
+  double eps;
+} csfm_params;
+
+/* Build flags. */
+#define CSFM_BUILD_DEFAULT 0u
+#define CSFM_BUILD_NO_COMPACT 1u /* keep all 8 wavelet levels even if the text uses < 129 symbols */
+#define CSFM_BUILD_KEEP_SA 2u    /* keep the full suffix array on the device for csfm_get_sa */
+
+typedef struct {
+  uint64_t n;          /* text length (cs::IndexMeta::n, fm_index.hpp:15) */
+  uint32_t sigma;      /* distinct byte values present in the text */
+  uint32_t levels;     /* wavelet-matrix levels stored (8, or ceil(log2 sigma) when compacted) */
+  uint32_t ssa_stride; /* SA sample stride (cs::SSA::stride) */
+  uint32_t device;     /* CUDA device ordinal */
+  uint64_t nsamp;      /* number of SA samples = ceil(n / stride) */
+  uint64_t blocks_per_level; /* 64-byte lines per level */
+  uint64_t blob_bytes; /* size of the device-resident index */
+  uint32_t has_sa;     /* full SA still resident (CSFM_BUILD_KEEP_SA) */
+  uint32_t reserved;
+} csfm_index_info;
+
+/* Counters describing the most recent query call on this handle (for bench accounting). */
+typedef struct {
+  uint64_t kernel_launches; /* CUDA kernels this library launched in the call */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t search_steps;    /* executed backward-search steps (S of SURVEY §8d); 0 unless asked */
+  uint64_t lf_steps;        /* LF steps walked by locate; 0 unless asked */
+  float kernel_ms;          /* device time of the dominant kernel (CUDA events), 0 unless asked */
+  uint32_t reserved;
+} csfm_call_stats;
+
+CSFM_API const char* csfm_last_error(void);
+CSFM_API const char* csfm_version(void);
+CSFM_API int csfm_device_count(int* count);
+
+/* ---- construction: replaces cs::FMIndex::build_from_text (fm_index.cpp:16-69) ------------- */
+
+/* text: n host bytes. Runs SA -> BWT -> C -> wavelet matrix -> SSA entirely on the device
+ * (prefix-doubling radix sort; order of build_sa_naive, sais.hpp:8-16). */
+CSFM_API int csfm_build_from_text(const uint8_t* text, uint64_t n, const csfm_params* params,
+                                  int device, uint32_t flags, csfm_index** out);
+/* Same, text already resident on `device`. */
+CSFM_API int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n,
+                                         const csfm_params* params, int device, uint32_t flags,
+                                         csfm_index** out);
+/* From build products computed elsewhere (host pointers): BWT (bwt.hpp:7-15) and the sampled SA
+ * (samples[k] = SA[k*stride], fm_index.cpp:57-65). C and the wavelet matrix are derived here. */
+CSFM_API int csfm_build_from_parts(const uint8_t* bwt, uint64_t n, const uint32_t* ssa,
+                                   uint64_t nsamp, uint32_t ssa_stride, int device,
+                                   uint32_t flags, csfm_index** out);
+CSFM_API void csfm_destroy(csfm_index* idx);
+CSFM_API int csfm_info(const csfm_index* idx, csfm_index_info* out);
+
+/* ---- build products back to the host (verification, .csidx writer, CPU baseline) ---------- */
+CSFM_API int csfm_get_C(const csfm_index* idx, uint32_t C[257]);           /* fm_index.cpp:36-47 */
+CSFM_API int csfm_get_ssa(const csfm_index* idx, uint32_t* out /*nsamp*/); /* fm_index.cpp:57-65 */
+CSFM_API int csfm_get_sa(const csfm_index* idx, uint32_t* out /*n*/);      /* needs KEEP_SA */
+CSFM_API int csfm_release_sa(csfm_index* idx);
+/* BWT re-derived from the wavelet matrix by an access kernel (wavelet.cpp:102-128). */
+CSFM_API int csfm_extract_bwt(const csfm_index* idx, uint8_t* out /*n*/);
+
+/* ---- replication: the whole index is one contiguous device blob --------------------------- */
+/* Pointer/size of the blob on the index's device. Broadcast it (one ncclBroadcast) and attach. */
+CSFM_API int csfm_blob(const csfm_index* idx, const void** d_blob, uint64_t* bytes);
+/* Wraps a blob already resident on `device` (e.g. the receive buffer of the broadcast). With
+ * take_ownership == 0 the caller keeps the memory alive for the life of the handle. */
+CSFM_API int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownership,
+                              csfm_index** out);
+/* Host round trip of the same blob (checkpoint / .csidx device-layout section). */
+CSFM_API int csfm_blob_to_host(const csfm_index* idx, void* out, uint64_t bytes);
+CSFM_API int csfm_from_host_blob(const void* blob, uint64_t bytes, int device, csfm_index** out);
+
+/* ---- queries: replace cs::FMIndex::count (fm_index.cpp:79-101) ----------------------------- */
+/* counts[q] = count(pattern q). sp_ep (nullable) receives the interval [sp,ep) after the last
+ * executed step, (0,0) for empty patterns and empty results. */
+CSFM_API int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs,
+                              uint64_t npat, uint64_t* counts, uint64_t* sp_ep);
+CSFM_API int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes,
+                                     const uint64_t* d_offs, uint64_t npat, uint64_t* d_counts,
+                                     uint64_t* d_sp_ep, void* stream);
+
+/* ---- queries: replace cs::FMIndex::locate (fm_index.cpp:107-157) --------------------------- */
+/* For query q the positions (SA-row order, at most `limit`) are out_pos[out_offs[q] ..
+ * out_offs[q+1]). status[q] is a csfm_query_status; positions of a failed query are
+ * unspecified. *total = out_offs[npat]. If cap < total nothing is written to out_pos and
+ * CSFM_ERR_CAPACITY is returned with out_offs and *total filled (call again with room);
+ * out_pos == NULL && cap == 0 is the sizing call and returns CSFM_OK. */
+CSFM_API int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs,
+                               uint64_t npat, uint64_t limit, uint64_t* out_offs,
+                               uint64_t* out_pos, uint64_t cap, int32_t* status,
+                               uint64_t* total);
+/* Device variant. Synchronises `stream` once (the total is needed to check cap). */
+CSFM_API int csfm_locate_batch_device(csfm_index* idx, const uint8_t* d_bytes,
+                                      const uint64_t* d_offs, uint64_t npat, uint64_t limit,
+                                      uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t cap,
+                                      int32_t* d_status, uint64_t* total, void* stream);
+
+/* ---- accounting -------------------------------------------------------------------------- */
+/* Enable per-call instrumentation (bit 0: count executed steps; bit 1: time the dominant
+ * kernel with CUDA events). Off by default; costs one extra reduction / two events. */
+CSFM_API int csfm_set_instrumentation(csfm_index* idx, uint32_t mask);
+CSFM_API int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out);
+
+/* ---- pinned host memory for batch buffers ------------------------------------------------- */
+CSFM_API int csfm_host_alloc(void** p, uint64_t bytes);
+CSFM_API int csfm_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSFM_H */

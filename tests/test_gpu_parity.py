@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA engine (through the C ABI, include/csfm.h) against
+ (a) the committed golden vectors produced by the unmodified reference, and
+ (b) the CPU oracle on seeded inputs, bit-exact: counts, [sp,ep), positions in SA-row order,
+     per-query status, and the build products (SA, BWT, C, SSA)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FM = json.load(open(os.path.join(GOLDEN, "golden_fm.json")))
+
+
+@pytest.fixture(scope="module")
+def fm():
+    import csfm_b200
+    csfm_b200.lib()  # raises if libcsfm.so is missing: there is no fallback to test instead
+    return csfm_b200
+
+
+def _check_queries(fm, idx, case):
+    pats = [bytes.fromhex(q["pat_hex"]) for q in case["queries"]]
+    d, o = fm.pack_patterns(pats)
+    counts = idx.count_batch(d, o)
+    for q, c in zip(case["queries"], counts):
+        assert int(c) == q["count"], (case["name"], q["pat_hex"])
+    for lim in sorted({q["limit"] for q in case["queries"]}):
+        sel = [q for q in case["queries"] if q["limit"] == lim]
+        d, o = fm.pack_patterns([bytes.fromhex(q["pat_hex"]) for q in sel])
+        offs, pos, status = idx.locate_batch(d, o, limit=lim)
+        for k, q in enumerate(sel):
+            assert int(status[k]) == q["status"], (case["name"], q["pat_hex"], lim)
+            if q["status"] == 0:
+                got = pos[int(offs[k]):int(offs[k + 1])].tolist()
+                assert got == q["locate"], (case["name"], q["pat_hex"], lim)
+    # single-query API mirrors the reference's exceptions
+    for q in case["queries"][:6]:
+        pat = bytes.fromhex(q["pat_hex"])
+        assert idx.count(pat) == q["count"]
+        if q["status"] == 0:
+            assert idx.locate(pat, q["limit"]) == q["locate"]
+        else:
+            with pytest.raises(RuntimeError, match="LF walk exceeded text length"):
+                idx.locate(pat, q["limit"])
+
+
+@pytest.mark.parametrize("case", FM["cases"], ids=[c["name"] for c in FM["cases"]])
+@pytest.mark.parametrize("flags", [0, 1], ids=["compact", "8levels"])
+def test_golden_from_text(fm, case, flags):
+    """build_from_text on the GPU (SA -> BWT -> C -> wavelet -> SSA) + queries vs the reference."""
+    text = bytes.fromhex(case["text_hex"])
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=case["stride"]), flags=flags | fm.BUILD_KEEP_SA)
+    info = idx.info()
+    assert info.n == case["n"]
+    assert info.levels == 8 or flags == 0
+    assert idx.C_array().tolist() == case["C"]
+    assert idx.ssa().tolist() == case["ssa"]
+    assert idx.bwt().tobytes() == bytes.fromhex(case["bwt_hex"])
+    if "sa" in case:
+        assert idx.sa().tolist() == case["sa"]
+    _check_queries(fm, idx, case)
+    assert idx.extract(1, 3) == text[1:4]
+
+
+@pytest.mark.parametrize("case", FM["cases"][:12], ids=[c["name"] for c in FM["cases"][:12]])
+def test_golden_from_parts(fm, case):
+    """csfm_build_from_parts: reference BWT + SSA in, same answers out."""
+    if case["n"] == 0:
+        pytest.skip("nothing to inject")
+    idx = fm.FMIndex.from_parts(bytes.fromhex(case["bwt_hex"]), np.array(case["ssa"], np.uint32), case["stride"])
+    _check_queries(fm, idx, case)
+
+
+def test_c1_benchmark_workload(fm):
+    """BASELINE.json configs[0] (tools/benchmark.cpp) with the reference's total_matches checksums."""
+    z = np.load(os.path.join(GOLDEN, "c1_workload.npz"))
+    text = z["text"]
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(), flags=fm.BUILD_KEEP_SA)
+    assert (idx.sa() == z["sa"]).all()
+    assert (idx.ssa() == z["ssa"]).all()
+    assert (idx.C_array() == z["C"]).all()
+    d, o = fm.pack_patterns([text[p:p + 5].tobytes() for p in z["rand_pos"]])
+    counts = idx.count_batch(d, o)
+    assert (counts == z["rand_count"]).all()
+    assert int(counts.sum()) == 9907582
+    freq = [bytes(p)[:l] for p, l in zip(z["freq_patterns"], z["freq_len"])]
+    d, o = fm.pack_patterns([freq[i % 10] for i in range(10000)])
+    fcounts = idx.count_batch(d, o)
+    assert int(fcounts.sum()) == 16309000
+    d, o = fm.pack_patterns([freq[i % 10] for i in range(100)])
+    offs, pos, status = idx.locate_batch(d, o, limit=100000)
+    assert (status == 0).all() and int(offs[-1]) == 163090
+    for q in range(100):
+        a = pos[int(offs[q]):int(offs[q + 1])]
+        assert a.size == z["loc_n"][q % 10]
+        assert int(a.sum()) == int(z["loc_sum"][q % 10])
+        assert int(np.bitwise_xor.reduce(a)) == int(z["loc_xor"][q % 10])
+        assert a[:8].tolist() == z["loc_first"][q % 10][: a.size].tolist()
+
+
+def _rand_text(rng, n, sigma, term):
+    alpha = np.sort(rng.choice(np.arange(1, 256), sigma, replace=False)).astype(np.uint8) if sigma < 256 \
+        else np.arange(256, dtype=np.uint8)
+    body = alpha[rng.integers(0, sigma, n)].astype(np.uint8)
+    return (np.concatenate([body, np.zeros(1, np.uint8)]) if term else body), alpha
+
+
+def _mixed_patterns(rng, text, alpha, k, maxlen):
+    pats = []
+    for _ in range(k):
+        m = int(rng.integers(1, maxlen + 1))
+        r = rng.random()
+        if r < 0.6 and text.size > m:
+            s = int(rng.integers(0, text.size - m))
+            pats.append(text[s:s + m].tobytes())
+        elif r < 0.9:
+            pats.append(alpha[rng.integers(0, alpha.size, m)].astype(np.uint8).tobytes())
+        else:
+            pats.append(rng.integers(0, 256, m, dtype=np.uint8).tobytes())  # bytes outside the alphabet
+    pats += [b"", text[-3:].tobytes(), text[:1].tobytes()]
+    return pats
+
+
+@pytest.mark.parametrize("sigma,n,stride,term,flags", [
+    (2, 50_000, 4, True, 0), (4, 200_000, 32, True, 0), (4, 200_000, 32, True, 1), (5, 100_000, 7, False, 0),
+    (21, 150_000, 16, True, 0), (97, 120_000, 32, True, 0), (256, 300_000, 32, True, 0), (256, 65_537, 1, False, 0),
+    (1, 5_000, 3, True, 0), (3, 479, 2, True, 0), (3, 480, 2, True, 0), (3, 481, 2, False, 0), (3, 961, 5, True, 0),
+])
+def test_random_vs_oracle(fm, sigma, n, stride, term, flags):
+    rng = np.random.default_rng(1000 * sigma + n + stride)
+    text, alpha = _rand_text(rng, n, sigma, term)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=flags | fm.BUILD_KEEP_SA)
+    orc = oracle.OracleIndex(text, stride=stride)
+    assert (idx.sa() == orc.sa).all()
+    assert (idx.bwt() == orc.bwt).all()
+    assert (idx.C_array() == orc.C).all()
+    assert (idx.ssa() == orc.ssa).all()
+    pats = _mixed_patterns(rng, text, alpha, 3000, 24)
+    d, o = fm.pack_patterns(pats)
+    idx.set_instrumentation(1)
+    counts, sp_ep = idx.count_batch(d, o, want_intervals=True)
+    steps_gpu = idx.last_call_stats().search_steps
+    oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
+    assert (counts == oc).all()
+    assert (sp_ep == ose).all()
+    assert steps_gpu == int(osteps.sum())  # the S of the roofline model is counted exactly
+    for limit in (100000, 7):
+        offs, pos, status = idx.locate_batch(d, o, limit=limit)
+        lf_gpu = idx.last_call_stats().lf_steps
+        ooffs, opos, ostatus, olf = orc.locate_batch(d, o, limit=limit)
+        assert (offs == ooffs).all()
+        assert (status == ostatus).all()
+        ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
+        assert (pos[ok] == opos[ok]).all()
+        if (ostatus == 0).all():
+            assert lf_gpu == olf
+
+
+def test_long_and_many_patterns(fm):
+    rng = np.random.default_rng(99)
+    text, alpha = _rand_text(rng, 400_000, 4, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32))
+    orc = oracle.OracleIndex(text, stride=32, sa=None)
+    # very long patterns (beyond any staging buffer) and a batch much larger than the grid
+    pats = [text[s:s + m].tobytes() for s, m in zip(rng.integers(0, 300_000, 64), rng.integers(500, 5000, 64))]
+    pats += [text[s:s + 12].tobytes() for s in rng.integers(0, 399_000, 200_000)]
+    d, o = fm.pack_patterns(pats)
+    counts, sp_ep = idx.count_batch(d, o, want_intervals=True)
+    oc, ose = orc.count_batch(d, o)
+    assert (counts == oc).all() and (sp_ep == ose).all()
+    assert (counts >= 1).all()
+
+
+def test_empty_batch_and_empty_patterns(fm):
+    idx = fm.FMIndex.build_from_text(b"banana$", fm.BuildParams(ssa_stride=2))
+    d, o = fm.pack_patterns([])
+    assert idx.count_batch(d, o).size == 0
+    offs, pos, status = idx.locate_batch(d, o)
+    assert offs.tolist() == [0] and pos.size == 0
+    d, o = fm.pack_patterns([b"", b"", b"a", b""])
+    assert idx.count_batch(d, o).tolist() == [7, 7, 3, 7]  # count("") == n (fm_index.cpp:80)
+    offs, pos, status = idx.locate_batch(d, o)
+    assert offs.tolist() == [0, 0, 0, 3, 3]  # locate("") is empty (fm_index.cpp:109)
+    assert pos.tolist() == [5, 3, 1]
+
+
+def test_locate_capacity_contract(fm):
+    import ctypes as C
+    idx = fm.FMIndex.build_from_text(b"abababab$", fm.BuildParams(ssa_stride=4))
+    d, o = fm.pack_patterns([b"ab", b"b"])
+    out_offs = np.zeros(3, np.uint64)
+    pos = np.zeros(2, np.uint64)
+    status = np.zeros(2, np.int32)
+    total = C.c_uint64()
+    rc = fm.lib().csfm_locate_batch(idx._h, d.ctypes.data, o.ctypes.data, 2, 100, out_offs.ctypes.data, pos.ctypes.data, 2,
+                                    status.ctypes.data, C.byref(total))
+    assert rc == 5 and total.value == 8 and out_offs.tolist() == [0, 4, 8]  # CSFM_ERR_CAPACITY
+
+
+def test_blob_round_trip_and_attach(fm):
+    import torch
+    rng = np.random.default_rng(5)
+    text, alpha = _rand_text(rng, 70_000, 6, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16))
+    pats = _mixed_patterns(rng, text, alpha, 500, 16)
+    d, o = fm.pack_patterns(pats)
+    want_c = idx.count_batch(d, o)
+    want_l = idx.locate_batch(d, o, limit=20)
+    blob = idx.blob_to_host()
+    idx2 = fm.FMIndex.from_host_blob(blob)
+    assert (idx2.count_batch(d, o) == want_c).all()
+    # replication path: device blob -> another device buffer (what the NCCL broadcast fills) -> attach
+    ptr, nbytes = idx.blob()
+    t = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
+    t.copy_(torch.from_numpy(blob))
+    idx3 = fm.FMIndex.attach_blob(t.data_ptr(), nbytes, 0, keepalive=t)
+    got = idx3.locate_batch(d, o, limit=20)
+    for a, b in zip(got, want_l):
+        assert (a == b).all()
+    bad = blob.copy()
+    bad[0] ^= 0xFF
+    with pytest.raises(fm.CsfmError):
+        fm.FMIndex.from_host_blob(bad)
+
+
+def test_device_pointer_api(fm):
+    import torch
+    rng = np.random.default_rng(11)
+    text, alpha = _rand_text(rng, 90_000, 4, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=8))
+    orc = oracle.OracleIndex(text, stride=8)
+    pats = _mixed_patterns(rng, text, alpha, 4000, 20)
+    d, o = fm.pack_patterns(pats)
+    npat = o.size - 1
+    dev = torch.device("cuda:0")
+    td = torch.from_numpy(d).to(dev)
+    to = torch.from_numpy(o.astype(np.int64)).to(dev)
+    tc = torch.zeros(npat, dtype=torch.int64, device=dev)
+    tse = torch.zeros(2 * npat, dtype=torch.int64, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        idx.count_batch_device(td.data_ptr(), to.data_ptr(), npat, tc.data_ptr(), tse.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    oc, ose = orc.count_batch(d, o)
+    assert (tc.cpu().numpy().astype(np.uint64) == oc).all()
+    assert (tse.cpu().numpy().astype(np.uint64).reshape(-1, 2) == ose).all()
+    toffs = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
+    tst = torch.zeros(npat, dtype=torch.int32, device=dev)
+    total = idx.locate_batch_device(td.data_ptr(), to.data_ptr(), npat, 9, toffs.data_ptr(), 0, 0, tst.data_ptr(), s.cuda_stream)
+    tpos = torch.zeros(max(1, total), dtype=torch.int64, device=dev)
+    total2 = idx.locate_batch_device(td.data_ptr(), to.data_ptr(), npat, 9, toffs.data_ptr(), tpos.data_ptr(), total,
+                                     tst.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=9)
+    assert total == total2 == int(ooffs[-1])
+    assert (toffs.cpu().numpy().astype(np.uint64) == ooffs).all()
+    assert (tpos.cpu().numpy().astype(np.uint64)[:total] == opos).all()
+    assert (tst.cpu().numpy() == ostatus).all()
