@@ -1,0 +1,494 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FM-index count() hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (default c3 = BASELINE.json configs[2], the configuration the metric's target is quoted
+on): 2^30-byte synthetic text over bytes 1..255 + 0x00 terminator (sigma = 256, 8 wavelet levels),
+text-sampled patterns of length 8..32, processed in 1 M-pattern batches. A "step" is one pass of
+count_batch over one 1 M-pattern batch per GPU (weak scaling: every rank runs its own batches
+against its own replica of the index; the index is built once on rank 0 and replicated with one
+NCCL broadcast of the device blob).
+
+One JSON line on stdout (rank 0):
+  value      whole-job count queries/s with the batches already resident in HBM (CUDA events)
+  e2e        the same through the host-pointer C ABI (csfm_count_batch): pinned host buffers,
+             H2D of patterns+offsets and D2H of the counts inside the timed region
+  roofline   algorithmic bytes (executed backward-search steps x 2 x L x 64 B) over
+             the mean kernel duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the UNMODIFIED reference cs::FMIndex::count (oracle/_ref/libcsref.so) on all host
+             cores over a bounded sample of the same batch, checked bit-exact against the GPU
+
+--impl reference times only that CPU reference (rank 0; other ranks exit 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import struct
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: text kind/seed, pattern lengths, seeds
+    "c3": dict(n_log2=30, kind="byte", seed_text=3, len_lo=8, len_hi=32, seed_len=4, seed_pos=5, batch=1_000_000,
+               stride=32, desc="C3: 2^30 B text sigma=256 (8 levels), text-sampled patterns len 8..32, 1M-pattern batches"),
+    "c2": dict(n_log2=26, kind="dna", seed_text=1, len_lo=20, len_hi=20, seed_len=0, seed_pos=2, batch=1_000_000,
+               stride=32, desc="C2: 2^26 B DNA+$ text (3 levels after alphabet compaction), text-sampled patterns len 20"),
+}
+METRIC = "count queries/sec"
+NB = 8  # distinct resident batches cycled through the timed steps (8 x ~28 MB > L2 with the 1.15 GB index)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, torch_device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = int(vis.split(",")[torch_device_index]) if vis and vis.split(",")[0].isdigit() else torch_device_index
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self._h is not None:
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._h is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class _DevMem:
+    """Exposes a raw device pointer to torch.as_tensor (zero-copy view of the index blob)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_text(wl, n, device):
+    from csfm_b200 import workloads as w
+    return (w.byte_text_torch if wl["kind"] == "byte" else w.dna_text_torch)(n, wl["seed_text"], device)
+
+
+def make_batch(wl, text, first, npat):
+    from csfm_b200 import workloads as w
+    return w.sampled_patterns_torch(text, npat, wl["len_lo"], wl["len_hi"], wl["seed_len"], wl["seed_pos"], first=first)
+
+
+def planes_from_blob(blob: np.ndarray):
+    """Device blob (8 levels of 64-byte lines) -> the reference's packed u64 bit planes."""
+    magic, version, levels, n, sigma, stride, nsamp, nblk, off_levels, level_stride, off_ssa, total = struct.unpack_from(
+        "<8sIIQIIQQQQQQ", blob, 0)
+    assert magic == b"CSFMDEV1" and levels == 8
+    nwords = (n + 63) // 64
+    planes = []
+    for l in range(8):
+        lines = blob[off_levels + l * level_stride: off_levels + l * level_stride + nblk * 64].view(np.uint32).reshape(nblk, 16)
+        payload = np.ascontiguousarray(lines[:, 1:]).reshape(-1)
+        if payload.size % 2:
+            payload = np.concatenate([payload, np.zeros(1, np.uint32)])
+        planes.append(payload.view(np.uint64)[:nwords].copy())
+    return n, planes
+
+
+def build_reference_index(fm, text, wl):
+    """UNMODIFIED cs::FMIndex (oracle/_ref) over the same text. The O(n^2 log n) build_sa_naive cannot
+    run at this size, so the BWT comes from the GPU builder (untimed setup) and the reference's own
+    BitVector::build_from_words builds its rank directory over the bit planes."""
+    import torch
+    import oracle
+    n = text.numel()
+    idx8 = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]),
+                                             device=text.device.index, flags=fm.BUILD_NO_COMPACT)
+    blob = idx8.blob_to_host()
+    idx8.close()
+    n2, planes = planes_from_blob(blob)
+    del blob
+    assert n2 == n
+    hist = np.zeros(256, np.uint64)  # C array from the text's own histogram, independent of the engine
+    for s0 in range(0, n, 1 << 27):
+        hist += torch.bincount(text[s0: s0 + (1 << 27)].int(), minlength=256).cpu().numpy().astype(np.uint64)
+    Carr = np.zeros(257, np.uint32)
+    Carr[1:] = np.cumsum(hist).astype(np.uint32)
+    return oracle.RefIndex(planes=planes, C_array=Carr, n=n, stride=wl["stride"])
+
+
+def reference_timed_sample(ref, data, offs, budget_s, nthreads, min_queries=None):
+    """Runs the reference's count() over the first q queries of a batch, q sized to ~budget_s."""
+    q0 = min(offs.size - 1, max(nthreads, min_queries or 0, 8))
+    t = time.perf_counter()
+    out0 = ref.count_batch(data, offs[: q0 + 1], nthreads=nthreads)
+    dt0 = time.perf_counter() - t
+    rate = q0 / max(dt0, 1e-9)
+    q = int(min(offs.size - 1, max(q0, rate * budget_s)))
+    if q <= q0 * 1.5:
+        return out0, q0, dt0
+    t = time.perf_counter()
+    out = ref.count_batch(data, offs[: q + 1], nthreads=nthreads)
+    return out, q, time.perf_counter() - t
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+    import csfm_b200 as fm
+    import oracle
+    wl = dict(WORKLOADS[args.workload])
+    n = 1 << (args.n_log2 or wl["n_log2"])
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    text = make_text(wl, n, dev)
+    ref = build_reference_index(fm, text, wl)
+    nthreads = os.cpu_count() or 1
+    bytes_d, offs_d = make_batch(wl, text, 0, min(wl["batch"], 200_000))
+    data, offs = bytes_d.cpu().numpy(), offs_d.cpu().numpy().astype(np.uint64)
+    # calibrate the per-step sample so that (steps + warmup) samples fit in ~90 s
+    _, q0, dt0 = reference_timed_sample(ref, data, offs, 0.0, nthreads)
+    per_step = max(nthreads, int((q0 / dt0) * 90.0 / (args.steps + args.warmup)))
+    per_step = min(per_step, (offs.size - 1) // 2)
+    total_q, total_t, cursor = 0, 0.0, 0
+    for i in range(args.warmup + args.steps):
+        lo = cursor % (offs.size - 1 - per_step)
+        o = offs[lo: lo + per_step + 1]
+        t = time.perf_counter()
+        ref.count_batch(data, o, nthreads=nthreads)
+        dt = time.perf_counter() - t
+        cursor += per_step
+        if i >= args.warmup:
+            total_q += per_step
+            total_t += dt
+    qps = total_q / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "n": n, "queries_per_step": per_step,
+                   "note": "reference cs::FMIndex::count verbatim on host cores; its index is injected from the GPU-built "
+                           "BWT (untimed setup) because build_sa_naive is O(n^2 log n)"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": nthreads, "kind": "reference",
+                         "sample": f"{per_step} queries per step x {args.steps} steps of the first batch, std::thread x {nthreads}"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine arm
+# ------------------------------------------------------------------------------------------------
+def run_engine(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import csfm_b200 as fm
+
+    wl = dict(WORKLOADS[args.workload])
+    n = 1 << (args.n_log2 or wl["n_log2"])
+    batch = args.batch or wl["batch"]
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    fm.lib()  # fail loudly if the CUDA extension is missing
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- text + index (rank 0 builds, one broadcast replicates) ------------------------------------
+    t0 = time.perf_counter()
+    text = make_text(wl, n, dev)
+    torch.cuda.synchronize()
+    t_text = time.perf_counter() - t0
+    build_s = bcast_ms = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+    if world > 1:
+        nbytes_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        if rank == 0:
+            ptr, nbytes = idx.blob()
+            nbytes_t[0] = nbytes
+        dist.broadcast(nbytes_t, 0)
+        nbytes = int(nbytes_t.item())
+        blob_t = torch.as_tensor(_DevMem(ptr, nbytes), device=dev) if rank == 0 else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(blob_t, 0)  # the one ncclBroadcast of the path
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+        if rank != 0:
+            idx = fm.FMIndex.attach_blob(blob_t.data_ptr(), nbytes, local_rank, keepalive=blob_t)
+    info = idx.info()
+    L = int(info.levels)
+    log(f"[rank {rank}] n={n} levels={L} sigma={info.sigma} blob={info.blob_bytes/1e6:.1f} MB text_gen={t_text:.2f}s "
+        f"build={build_s if build_s is None else round(build_s, 2)}s bcast_ms={bcast_ms}")
+
+    # ---- batches: NB distinct batches per rank, resident on the device and mirrored in pinned host memory
+    d_batches, h_batches = [], []
+    for b in range(NB):
+        first = (b * world + rank) * batch
+        bytes_d, offs_d = make_batch(wl, text, first, batch)
+        d_batches.append((bytes_d, offs_d))
+        hb = torch.empty(bytes_d.numel(), dtype=torch.uint8).pin_memory()
+        ho = torch.empty(offs_d.numel(), dtype=torch.int64).pin_memory()
+        hb.copy_(bytes_d)
+        ho.copy_(offs_d)
+        h_batches.append((hb, ho))
+    d_counts = torch.zeros(batch, dtype=torch.int64, device=dev)
+    h_counts = torch.zeros(batch, dtype=torch.int64).pin_memory()
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+
+    def step_device(b):
+        bytes_d, offs_d = d_batches[b % NB]
+        idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), batch, d_counts.data_ptr(), 0, stream.cuda_stream)
+
+    # exact executed-step counts per batch (S of the roofline model) + correctness properties
+    idx.set_instrumentation(1)
+    steps_per_batch = []
+    for b in range(NB):
+        step_device(b)
+        stream.synchronize()
+        steps_per_batch.append(int(idx.last_call_stats().search_steps))
+        if b == 0:
+            c0 = d_counts.cpu().numpy().copy()
+            assert (c0 >= 1).all(), "text-sampled patterns must occur at least once"
+    idx.set_instrumentation(0)
+
+    # ---- timed region 1: device-resident inputs -----------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        with torch.cuda.stream(stream):
+            for i in range(args.steps):
+                evs[i].record(stream)
+                step_device(i)
+            evs[args.steps].record(stream)
+        stream.synchronize()
+        torch.cuda.synchronize()
+    barrier()
+    total_ms = evs[0].elapsed_time(evs[args.steps])
+    step_ms = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)])
+    launches = args.steps * 1  # one count_kernel per step (the 32-byte cursor memset is not a kernel)
+
+    # ---- timed region 2: end to end through the host-pointer C ABI ------------------------------------
+    L_ = fm.lib()
+
+    def step_e2e(b):
+        hb, ho = h_batches[b % NB]
+        rc = L_.csfm_count_batch(idx._h, hb.data_ptr(), ho.data_ptr(), batch, h_counts.data_ptr(), None)
+        if rc != 0:
+            raise RuntimeError(L_.csfm_last_error().decode())
+
+    for i in range(max(3, args.warmup // 2)):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_steps = args.steps
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    st = idx.last_call_stats()
+    h2d, d2h = int(st.h2d_bytes), int(st.d2h_bytes)
+    step_device(e2e_steps - 1)  # same batch as the last end-to-end step: both paths must agree
+    stream.synchronize()
+    e2e_equal = bool((h_counts.numpy() == d_counts.cpu().numpy()).all())
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    value = world * args.steps * batch / (total_ms / 1e3)
+    e2e_value = world * e2e_steps * batch / e2e_s
+
+    # ---- roofline of the dominant kernel (count_kernel) ------------------------------------------------
+    peak, peak_src = measured_peak()
+    alg_bytes = [steps_per_batch[i % NB] * 2 * L * 64 for i in range(args.steps)]
+    achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
+                "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
+                "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
+                "note": "duration per launch = CUDA events on the launching stream around each step "
+                        "(32-byte cursor memset + count_kernel)"}
+
+    # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, checked vs the GPU
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            if not oracle.ref_available():
+                raise RuntimeError("oracle/_ref/libcsref.so missing")
+            nthreads = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            ref = build_reference_index(fm, text, wl)
+            t_inject = time.perf_counter() - t0
+            hb, ho = h_batches[0]
+            data, offs = hb.numpy(), ho.numpy().astype(np.uint64)
+            out, q, dt = reference_timed_sample(ref, data, offs, args.cpu_budget, nthreads)
+            ok = bool((out[:q] == c0[:q].astype(np.uint64)).all())
+            cpu = {"value": q / dt, "unit": "queries/s", "cores": nthreads, "kind": "reference",
+                   "sample": f"first {q} queries of batch 0 in {dt:.1f} s on {nthreads} std::threads (reference index injected in {t_inject:.0f} s)",
+                   "bit_exact_vs_gpu": ok}
+            if not ok:
+                log("ERROR: GPU counts differ from the reference on the sampled queries")
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "n": n, "levels": L, "sigma": int(info.sigma), "batch_per_gpu": batch,
+                   "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
+                   "l2_policy": "inputs larger than L2: 1.15 GB index + a different 28 MB batch every step" if n >= (1 << 29)
+                   else "index is L2-resident at this size; a different batch every step",
+                   "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"])},
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "csfm_count_batch (host pointers, pinned)"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "clocks": clocks.summary(),
+        "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-log2", type=int, default=None, help="override text size (reduced sizes are flagged in config)")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one process per GPU)")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_engine(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,5 +1,6 @@
 """Import shim: the package directory name contains hyphens (it mirrors the reference repo's
 name), so it is loaded by path and re-exported here as ``csfm_b200``."""
+import importlib
 import importlib.util
 import os
 import sys
@@ -16,4 +17,5 @@ if _NAME not in sys.modules:
     _spec.loader.exec_module(_mod)
 _mod = sys.modules[_NAME]
 globals().update({k: getattr(_mod, k) for k in dir(_mod) if not k.startswith("__")})
+workloads = importlib.import_module(_NAME + ".workloads")
 PACKAGE_DIR = _PKG_DIR

@@ -322,6 +322,8 @@ def ref():
         L.csref_inject.restype = vp
         L.csref_inject_bwt.argtypes = [_u8p, C.c_uint64, _u32p, C.c_uint64, C.c_uint32]
         L.csref_inject_bwt.restype = vp
+        L.csref_inject_planes.argtypes = [C.c_uint64, C.POINTER(_u64p), _u32p, _u8p, _u32p, C.c_uint64, C.c_uint32]
+        L.csref_inject_planes.restype = vp
         L.csref_destroy.argtypes = [vp]
         L.csref_n.argtypes = [vp]
         L.csref_n.restype = C.c_uint64
@@ -425,10 +427,22 @@ class RefWavelet:
 class RefIndex:
     """The compiled, unmodified cs::FMIndex."""
 
-    def __init__(self, text=None, stride=32, sa=None, bwt=None, ssa=None):
+    def __init__(self, text=None, stride=32, sa=None, bwt=None, ssa=None, planes=None, C_array=None, n=None):
         L = ref()
         self.stride = int(stride)
-        if bwt is not None:
+        if planes is not None:
+            # eight packed bit planes (u64, LSB-first) -> cs::BitVector::build_from_words
+            nwords = (int(n) + 63) // 64
+            keep = [np.ascontiguousarray(p[:nwords], dtype=np.uint64) for p in planes]
+            assert len(keep) == 8 and all(k.size == nwords for k in keep)
+            arr = (_u64p * 8)(*[_ptr(k, _u64p) for k in keep])
+            cc = np.ascontiguousarray(C_array, dtype=np.uint32)
+            b = _as_u8(bwt) if bwt is not None else None
+            s = np.ascontiguousarray(ssa, dtype=np.uint32) if ssa is not None else None
+            self._h = L.csref_inject_planes(int(n), arr, _ptr(cc, _u32p), _ptr(b, _u8p) if b is not None else None,
+                                            _ptr(s, _u32p) if s is not None else None,
+                                            s.size if s is not None else 0, self.stride)
+        elif bwt is not None:
             b = _as_u8(bwt)
             s = np.ascontiguousarray(ssa if ssa is not None else np.zeros(0), dtype=np.uint32)
             self._h = L.csref_inject_bwt(_ptr(b, _u8p), b.size, _ptr(s, _u32p) if s.size else None,

@@ -93,6 +93,30 @@ void* csref_inject_bwt(const uint8_t* bwt, uint64_t n, const uint32_t* samples, 
   return idx;
 }
 
+// Fast injection for n ~ 1e9 (wavelet_.build alone would take minutes there): the eight packed
+// bit planes are supplied by the caller and handed to the reference's own
+// cs::BitVector::build_from_words (src/core/bitvector.cpp:98-159), which builds the reference's
+// super/sub-block directory. tests/test_oracle_vs_reference.py checks that the resulting levels
+// are identical to the ones cs::WaveletTree::build produces. words[l] must hold exactly
+// ceil(n/64) u64 words. bwt/samples may be null when only count() will be called.
+void* csref_inject_planes(uint64_t n, const uint64_t* const* words, const uint32_t* C257,
+                          const uint8_t* bwt, const uint32_t* samples, uint64_t nsamp,
+                          uint32_t ssa_stride) {
+  auto* idx = new FMIndex();
+  idx->meta_.n = n;
+  idx->C_.assign(C257, C257 + 257);
+  idx->wavelet_.n_ = n;
+  const size_t nwords = (n + 63) / 64;
+  if (n) {
+    for (int l = 0; l < 8; ++l)
+      idx->wavelet_.levels_[l].build_from_words(std::vector<uint64_t>(words[l], words[l] + nwords), n);
+  }
+  if (bwt) idx->bwt_.assign(reinterpret_cast<const char*>(bwt), n);
+  idx->ssa_.stride = ssa_stride;
+  if (samples) idx->ssa_.samples.assign(samples, samples + nsamp);
+  return idx;
+}
+
 void csref_destroy(void* h) { delete static_cast<FMIndex*>(h); }
 
 uint64_t csref_n(void* h) { return static_cast<FMIndex*>(h)->meta_.n; }
