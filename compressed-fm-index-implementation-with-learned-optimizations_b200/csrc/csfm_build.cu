@@ -13,6 +13,7 @@
 //                  destination of symbol i is exactly the rank formula the queries use:
 //                  bit ? zeros + rank1(i) : i - rank1(i)   (wavelet.cpp:47-51)
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -195,6 +196,10 @@ int index_finish_handle(csfm_index* idx) {
   cudaDeviceProp prop;
   CSFM_CUDA(cudaGetDeviceProperties(&prop, idx->device));
   idx->num_sms = prop.multiProcessorCount;
+  if (const char* g = std::getenv("CSFM_L2_FETCH_GRANULARITY")) {  // experiment knob (32/64/128)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
+    cudaGetLastError();
+  }
   const BlobHeader& h = idx->h;
   IndexView& v = idx->view;
   v.levels = idx->d_blob + h.off_levels;
