@@ -15,7 +15,7 @@ One JSON line on stdout (rank 0):
   value      whole-job count queries/s with the batches already resident in HBM (CUDA events)
   e2e        the same through the host-pointer C ABI (csfm_count_batch): pinned host buffers,
              H2D of patterns+offsets and D2H of the counts inside the timed region
-  roofline   algorithmic bytes (executed backward-search steps x 2 x L x 64 B) over
+  roofline   algorithmic bytes (executed backward-search steps x 2 x L x line bytes) over
              the mean kernel duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline  the UNMODIFIED reference cs::FMIndex::count (oracle/_ref/libcsref.so) on all host
              cores over a bounded sample of the same batch, checked bit-exact against the GPU
@@ -41,9 +41,9 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: text kind/seed, pattern lengths, seeds
     "c3": dict(n_log2=30, kind="byte", seed_text=3, len_lo=8, len_hi=32, seed_len=4, seed_pos=5, batch=1_000_000,
-               stride=32, desc="C3: 2^30 B text sigma=256 (8 levels), text-sampled patterns len 8..32, 1M-pattern batches"),
+               stride=32, desc="C3: 2^30 B text sigma=256, text-sampled patterns len 8..32, 1M-pattern batches"),
     "c2": dict(n_log2=26, kind="dna", seed_text=1, len_lo=20, len_hi=20, seed_len=0, seed_pos=2, batch=1_000_000,
-               stride=32, desc="C2: 2^26 B DNA+$ text (3 levels after alphabet compaction), text-sampled patterns len 20"),
+               stride=32, desc="C2: 2^26 B DNA+$ text, text-sampled patterns len 20, 1M-pattern batches"),
 }
 METRIC = "count queries/sec"
 NB = 8  # distinct resident batches cycled through the timed steps (8 x ~28 MB > L2 with the 1.15 GB index)
@@ -168,7 +168,7 @@ def build_reference_index(fm, text, wl):
     import oracle
     n = text.numel()
     idx8 = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]),
-                                             device=text.device.index, flags=fm.BUILD_NO_COMPACT)
+                                             device=text.device.index, flags=fm.BUILD_NO_COMPACT | fm.BUILD_LAYOUT_BINARY64)
     blob = idx8.blob_to_host()
     idx8.close()
     n2, planes = planes_from_blob(blob)
@@ -273,7 +273,8 @@ def run_engine(args, rank, world, local_rank):
     build_s = bcast_ms = None
     if rank == 0:
         t0 = time.perf_counter()
-        idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank)
+        idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank,
+                                                flags=fm.BUILD_LAYOUT_BINARY64 if args.layout == 1 else 0)
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
     if world > 1:
@@ -391,7 +392,8 @@ def run_engine(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (count_kernel) ------------------------------------------------
     peak, peak_src = measured_peak()
-    alg_bytes = [steps_per_batch[i % NB] * 2 * L * 64 for i in range(args.steps)]
+    line_bytes = int(info.line_bytes)
+    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes for i in range(args.steps)]
     achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
@@ -435,7 +437,8 @@ def run_engine(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "n": n, "levels": L, "sigma": int(info.sigma), "batch_per_gpu": batch,
+        "config": {"workload": wl["desc"], "n": n, "levels": L, "line_bytes": int(info.line_bytes), "layout": int(info.layout),
+                   "sigma": int(info.sigma), "batch_per_gpu": batch,
                    "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
                    "l2_policy": "inputs larger than L2: 1.15 GB index + a different 28 MB batch every step" if n >= (1 << 29)
                    else "index is L2-resident at this size; a different batch every step",
@@ -460,6 +463,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n-log2", type=int, default=None, help="override text size (reduced sizes are flagged in config)")
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--layout", type=int, default=2, choices=[1, 2], help="2 = 16-ary levels / 128-byte lines (default), 1 = binary / 64-byte lines")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

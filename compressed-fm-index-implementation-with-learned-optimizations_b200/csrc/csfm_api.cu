@@ -190,6 +190,8 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->blocks_per_level = idx->h.nblk;
   out->blob_bytes = idx->blob_bytes;
   out->has_sa = idx->d_sa != nullptr;
+  out->layout = idx->h.layout;
+  out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;
   return CSFM_OK;
 }
 
@@ -255,10 +257,14 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
   BlobHeader h;
   CSFM_CUDA(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost));
-  if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 1) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
-  if (h.total_bytes > bytes || h.levels == 0 || h.levels > kMaxLevels || h.nblk != h.n / kPayloadBits + 1 ||
-      h.off_levels < sizeof(BlobHeader) || h.off_ssa + h.nsamp * 4 > h.total_bytes || h.stride == 0 ||
-      h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * kLineBytes)
+  if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 2) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
+  const bool nib = h.layout == kLayoutNibble128;
+  const uint64_t per_line = nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
+  if ((h.layout != kLayoutNibble128 && h.layout != kLayoutBinary64) || h.total_bytes > bytes || h.levels == 0 ||
+      h.levels > (nib ? 2u : kMaxLevels) || h.nblk != h.n / per_line + 1 || h.off_levels < sizeof(BlobHeader) ||
+      h.off_ssa + h.nsamp * 4 > h.total_bytes || h.stride == 0 ||
+      h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * line_bytes ||
+      h.nsamp != (h.n + h.stride - 1) / h.stride)
     return fail(CSFM_ERR_FORMAT, "inconsistent blob header");
   auto* idx = new (std::nothrow) csfm_index();
   if (!idx) return fail(CSFM_ERR_NOMEM, "host allocation failed");

@@ -1,17 +1,19 @@
-// csfm_build.cu — BWT -> device-resident wavelet-matrix index (the "wm_build" kernels).
+// csfm_build.cu — BWT -> device-resident index (the "wm_build" kernels), both layouts.
 //
 // Replaces cs::WaveletTree::build + cs::BitVector::build
 // (/root/reference/src/core/wavelet.cpp:14-53, src/core/bitvector.cpp:14-92) and the C-array
-// loop of FMIndex::build_from_text (src/api/fm_index.cpp:36-47). Same bit planes, different
-// container: 64-byte lines carrying their own absolute rank counter (csfm_common.cuh).
+// loop of FMIndex::build_from_text (src/api/fm_index.cpp:36-47). Layouts: csfm_common.cuh.
 //
-// Per level l (bit L-1-l of the compact symbol code):
-//   pack_level     one warp per 480-symbol line: 15 ballots -> 15 payload words + line popcount
-//   cub::ExclusiveSum over the line popcounts -> absolute rank before each line
-//   write_headers  word 0 of every line
-//   split_level    stable partition (zeros first, then ones) into the next level's order; the
-//                  destination of symbol i is exactly the rank formula the queries use:
-//                  bit ? zeros + rank1(i) : i - rank1(i)   (wavelet.cpp:47-51)
+// Layout 2 (nibble levels, 128-byte lines), per level:
+//   nib_pack      one warp per 128-symbol line: packs the 16 payload words, per-line histogram
+//                 of the 16 nibble values (match_any + shared counters)
+//   cub::ExclusiveSum x16 over the per-line histograms -> absolute counters
+//   nib_counters  writes the 16 counters of every line
+//   nib_split     (level 0 of a 2-level index) stable 16-way partition by the high nibble:
+//                 dst = start1[hi] + rank_0(hi, i) — the same formula the queries evaluate
+// Layout 1 (binary, 64-byte lines), per level (bit L-1-l of the code):
+//   pack_level / cub::ExclusiveSum / write_headers / split_level (stable 0/1 partition,
+//   dst = bit ? zeros + rank1(i) : i - rank1(i), wavelet.cpp:47-51)
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -65,6 +67,8 @@ __global__ void map_codes_kernel(const uint8_t* __restrict__ in, uint8_t* __rest
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     out[i] = sc[in[i]];
 }
+
+// ---- layout 1 -----------------------------------------------------------------------------
 
 // One warp per line. Writes words 1..15 (payload) and 0 into word 0; line popcount to pop[].
 __global__ void pack_level_kernel(const uint8_t* __restrict__ cur, uint64_t n, int bit,
@@ -124,6 +128,88 @@ __global__ void split_level_kernel(const uint8_t* __restrict__ cur, uint8_t* __r
   }
 }
 
+// ---- layout 2 -----------------------------------------------------------------------------
+constexpr int kWarpsPerBlock = 8;
+
+// u32 index inside a 128-byte line of payload word w (0..15) / counter v (0..15)
+__device__ __forceinline__ uint32_t line_word_of_payload(uint32_t w) { return 8u * (w >> 2) + 4u + (w & 3u); }
+__device__ __forceinline__ uint32_t line_word_of_counter(uint32_t v) { return 8u * (v >> 2) + (v & 3u); }
+
+// One warp per line: payload words + per-line histogram linecnt[v * nblk + b].
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+nib_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, int shift, uint8_t* __restrict__ level, uint64_t nblk,
+                uint32_t* __restrict__ linecnt) {
+  __shared__ uint32_t hist[kWarpsPerBlock][16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t b = warp; b < nblk; b += nwarps) {
+    if (lane < 16) hist[wib][lane] = 0;
+    __syncwarp();
+    uint32_t* line = reinterpret_cast<uint32_t*>(level + b * kLine2Bytes);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint64_t i = b * kSymsPerLine + 32 * r + lane;
+      const bool valid = i < n;
+      const uint32_t v = valid ? ((cur[i] >> shift) & 15u) : 0u;
+      // histogram: one shared add per distinct value per round
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? v : 0xFFu);
+      if (valid && lane == __ffs(peers) - 1) hist[wib][v] += __popc(peers);
+      // 8 consecutive lanes -> one payload word
+      uint32_t x = v << (4 * (lane & 7));
+      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 1);
+      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
+      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 4);
+      if ((lane & 7) == 0) line[line_word_of_payload(4 * r + (lane >> 3))] = x;
+      __syncwarp();
+    }
+    if (lane < 16) linecnt[(uint64_t)lane * nblk + b] = hist[wib][lane];
+    __syncwarp();
+  }
+}
+
+__global__ void nib_counters_kernel(uint8_t* __restrict__ level, uint64_t nblk, const uint32_t* __restrict__ prefix) {
+  const uint64_t total = nblk * 16;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint64_t b = t >> 4;
+    const uint32_t v = (uint32_t)(t & 15);
+    reinterpret_cast<uint32_t*>(level + b * kLine2Bytes)[line_word_of_counter(v)] = prefix[(uint64_t)v * nblk + b];
+  }
+}
+
+struct Start16 {
+  uint32_t s[16];
+};
+
+// Stable 16-way partition by the high nibble: element i of level 0 goes to
+// start1[hi] + rank_0(hi, i) in level 1.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+nib_split_kernel(const uint8_t* __restrict__ cur, uint8_t* __restrict__ nxt, uint64_t n, uint64_t nblk,
+                 const uint32_t* __restrict__ prefix, const __grid_constant__ Start16 st) {
+  __shared__ uint32_t run[kWarpsPerBlock][16];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t b = warp; b < nblk; b += nwarps) {
+    if (lane < 16) run[wib][lane] = st.s[lane] + prefix[(uint64_t)lane * nblk + b];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint64_t i = b * kSymsPerLine + 32 * r + lane;
+      const bool valid = i < n;
+      const uint8_t sym = valid ? cur[i] : 0;
+      const uint32_t hi = sym >> 4;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? hi : 0xFFu);
+      if (valid) nxt[(uint64_t)run[wib][hi] + __popc(peers & lt)] = sym;
+      __syncwarp();
+      if (valid && lane == __ffs(peers) - 1) run[wib][hi] += __popc(peers);
+      __syncwarp();
+    }
+  }
+}
+
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 uint32_t bit_reverse(uint32_t v, int bits) {
@@ -156,24 +242,51 @@ static void fill_tables(BlobHeader& h, const unsigned long long hist[256], uint3
     }
   }
   h.sigma = sigma;
-  uint32_t L = 8;
+  uint32_t B = 8;
   if (compact) {
-    L = 1;
-    while ((1u << L) < sigma) ++L;
+    B = 1;
+    while ((1u << B) < sigma) ++B;
   } else {
     for (int c = 0; c < 256; ++c) {
       h.code_of_byte[c] = (uint8_t)c;
       h.byte_of_code[c] = (uint8_t)c;
     }
   }
-  h.levels = L;
-  // path(code,0) = number of symbols whose L-bit-reversed code is smaller: after L stable
-  // 0/1 splits the sequence is ordered by the bit-reversed code (last split most significant).
-  const uint32_t ncodes = 1u << L;
-  std::vector<uint64_t> freq_by_rev(ncodes, 0);
-  std::vector<uint32_t> code_freq(ncodes, 0);
+  h.code_bits = B;
+  std::vector<uint32_t> code_freq(256, 0);
   for (int c = 0; c < 256; ++c)
     if (hist[c]) code_freq[h.code_of_byte[c]] += (uint32_t)hist[c];
+  std::memset(h.base_by_byte, 0, sizeof h.base_by_byte);
+  std::memset(h.base_by_code, 0, sizeof h.base_by_code);
+  std::memset(h.start1, 0, sizeof h.start1);
+
+  if (h.layout == kLayoutNibble128) {
+    h.levels = B <= 4 ? 1 : 2;
+    if (h.levels == 2) {
+      uint32_t acc = 0;
+      for (uint32_t g = 0; g < 16; ++g) {
+        h.start1[g] = acc;
+        for (uint32_t lo = 0; lo < 16; ++lo) acc += code_freq[(g << 4) | lo];
+      }
+    }
+    for (int c = 0; c < 256; ++c) {
+      if (!hist[c]) continue;
+      const uint32_t code = h.code_of_byte[c];
+      uint32_t before = 0;  // rank_1(lo, start1[hi]) = #{codes with a smaller hi and the same lo}
+      if (h.levels == 2)
+        for (uint32_t g = 0; g < (code >> 4); ++g) before += code_freq[(g << 4) | (code & 15u)];
+      h.base_by_byte[c] = h.C[c] - before;  // u32 wrap-around is intended
+      h.base_by_code[code] = h.C[c] - before;
+    }
+    return;
+  }
+
+  // layout 1: path(code,0) = number of symbols whose L-bit-reversed code is smaller: after L stable
+  // 0/1 splits the sequence is ordered by the bit-reversed code (last split most significant).
+  const uint32_t L = B;
+  h.levels = L;
+  const uint32_t ncodes = 1u << L;
+  std::vector<uint64_t> freq_by_rev(ncodes, 0);
   for (uint32_t code = 0; code < ncodes; ++code) freq_by_rev[bit_reverse(code, L)] = code_freq[code];
   std::vector<uint32_t> start_by_rev(ncodes, 0);
   uint32_t acc = 0;
@@ -181,8 +294,6 @@ static void fill_tables(BlobHeader& h, const unsigned long long hist[256], uint3
     start_by_rev[r] = acc;
     acc += (uint32_t)freq_by_rev[r];
   }
-  std::memset(h.base_by_byte, 0, sizeof h.base_by_byte);
-  std::memset(h.base_by_code, 0, sizeof h.base_by_code);
   for (int c = 0; c < 256; ++c) {
     if (!hist[c]) continue;
     const uint32_t code = h.code_of_byte[c];
@@ -196,10 +307,6 @@ int index_finish_handle(csfm_index* idx) {
   cudaDeviceProp prop;
   CSFM_CUDA(cudaGetDeviceProperties(&prop, idx->device));
   idx->num_sms = prop.multiProcessorCount;
-  if (const char* g = std::getenv("CSFM_L2_FETCH_GRANULARITY")) {  // experiment knob (32/64/128)
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
-    cudaGetLastError();
-  }
   const BlobHeader& h = idx->h;
   IndexView& v = idx->view;
   v.levels = idx->d_blob + h.off_levels;
@@ -210,6 +317,7 @@ int index_finish_handle(csfm_index* idx) {
   v.L = h.levels;
   v.stride = h.stride;
   v.nsamp = (uint32_t)h.nsamp;
+  v.layout = h.layout;
   for (int l = 0; l < (int)kMaxLevels; ++l) v.zeros[l] = h.zeros[l];
   if (!idx->stream) CSFM_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
   if (!idx->ev0) CSFM_CUDA(cudaEventCreate(&idx->ev0));
@@ -242,15 +350,17 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   BlobHeader& h = idx->h;
   std::memset(&h, 0, sizeof h);
   std::memcpy(h.magic, "CSFMDEV1", 8);
-  h.version = 1;
+  h.version = 2;
   h.n = n;
   h.stride = stride;
   h.nsamp = nsamp;
+  h.layout = (flags & CSFM_BUILD_LAYOUT_BINARY64) ? kLayoutBinary64 : kLayoutNibble128;
   fill_tables(h, hist, flags);
   const uint32_t L = h.levels;
-  h.nblk = n / kPayloadBits + 1;
+  const bool nib = h.layout == kLayoutNibble128;
+  h.nblk = nib ? n / kSymsPerLine + 1 : n / kPayloadBits + 1;
   h.off_levels = kHeaderBytes;
-  h.level_stride = align_up(h.nblk * kLineBytes, 256);
+  h.level_stride = align_up(h.nblk * (nib ? kLine2Bytes : kLineBytes), 256);
   h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
   h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
 
@@ -284,10 +394,11 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   } while (0)
 
   const uint64_t nbuf = n ? n : 1;
+  const uint64_t ncnt = h.nblk * (nib ? 16 : 1);  // per-line counters before / after the scan
   BUILD_CUDA(cudaMalloc(&d_cur, nbuf));
-  BUILD_CUDA(cudaMalloc(&d_nxt, nbuf));
-  BUILD_CUDA(cudaMalloc(&d_pop, h.nblk * 4));
-  BUILD_CUDA(cudaMalloc(&d_rank, h.nblk * 4));
+  if (L > 1) BUILD_CUDA(cudaMalloc(&d_nxt, nbuf));
+  BUILD_CUDA(cudaMalloc(&d_pop, ncnt * 4));
+  BUILD_CUDA(cudaMalloc(&d_rank, ncnt * 4));
   BUILD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, d_pop, d_rank, (int64_t)h.nblk, st));
   BUILD_CUDA(cudaMalloc(&d_scan_tmp, scan_tmp_bytes ? scan_tmp_bytes : 16));
 
@@ -296,24 +407,42 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
     std::memcpy(ct.code, h.code_of_byte, 256);
     map_codes_kernel<<<2048, 256, 0, st>>>(d_bwt, d_cur, n, ct);
   }
-  const int wpb = 8;  // warps per block
+  const int wpb = kWarpsPerBlock;
   const uint64_t want_blocks = (h.nblk + wpb - 1) / wpb;
   const int grid = (int)std::min<uint64_t>(want_blocks, 148ull * 64);
-  for (uint32_t l = 0; l < L; ++l) {
-    const int bit = (int)(L - 1 - l);
-    uint8_t* level = idx->d_blob + h.off_levels + (uint64_t)l * h.level_stride;
-    pack_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, bit, level, h.nblk, d_pop);
-    BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop, d_rank, (int64_t)h.nblk, st));
-    write_headers_kernel<<<1024, 256, 0, st>>>(level, h.nblk, d_rank);
-    uint32_t last_rank = 0, last_pop = 0;
-    BUILD_CUDA(cudaMemcpyAsync(&last_rank, d_rank + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
-    BUILD_CUDA(cudaMemcpyAsync(&last_pop, d_pop + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
-    BUILD_CUDA(cudaStreamSynchronize(st));
-    const uint32_t ones = last_rank + last_pop;
-    h.zeros[l] = (uint32_t)n - ones;
-    if (l + 1 < L && n) {
-      split_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, d_nxt, n, bit, h.nblk, d_rank, h.zeros[l]);
-      std::swap(d_cur, d_nxt);
+  if (nib) {
+    Start16 s16;
+    std::memcpy(s16.s, h.start1, sizeof s16.s);
+    for (uint32_t l = 0; l < L; ++l) {
+      const int shift = (L == 2 && l == 0) ? 4 : 0;
+      uint8_t* level = idx->d_blob + h.off_levels + (uint64_t)l * h.level_stride;
+      nib_pack_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, shift, level, h.nblk, d_pop);
+      for (int v = 0; v < 16; ++v)
+        BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop + (uint64_t)v * h.nblk,
+                                                 d_rank + (uint64_t)v * h.nblk, (int64_t)h.nblk, st));
+      nib_counters_kernel<<<2048, 256, 0, st>>>(level, h.nblk, d_rank);
+      if (l + 1 < L && n) {
+        nib_split_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, d_nxt, n, h.nblk, d_rank, s16);
+        std::swap(d_cur, d_nxt);
+      }
+    }
+  } else {
+    for (uint32_t l = 0; l < L; ++l) {
+      const int bit = (int)(L - 1 - l);
+      uint8_t* level = idx->d_blob + h.off_levels + (uint64_t)l * h.level_stride;
+      pack_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, bit, level, h.nblk, d_pop);
+      BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop, d_rank, (int64_t)h.nblk, st));
+      write_headers_kernel<<<1024, 256, 0, st>>>(level, h.nblk, d_rank);
+      uint32_t last_rank = 0, last_pop = 0;
+      BUILD_CUDA(cudaMemcpyAsync(&last_rank, d_rank + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
+      BUILD_CUDA(cudaMemcpyAsync(&last_pop, d_pop + (h.nblk - 1), 4, cudaMemcpyDeviceToHost, st));
+      BUILD_CUDA(cudaStreamSynchronize(st));
+      const uint32_t ones = last_rank + last_pop;
+      h.zeros[l] = (uint32_t)n - ones;
+      if (l + 1 < L && n) {
+        split_level_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, d_nxt, n, bit, h.nblk, d_rank, h.zeros[l]);
+        std::swap(d_cur, d_nxt);
+      }
     }
   }
   // 3) SA samples + header

@@ -1,53 +1,77 @@
-// csfm_common.cuh — device-resident index layout and the rank primitive shared by all kernels.
+// csfm_common.cuh — device-resident index layouts and the rank primitives shared by all kernels.
 //
-// Layout (replaces the reference's two-level super/sub-block directory,
-// /root/reference/src/core/bitvector.hpp:94-99, and its 8 std::vector-backed levels,
-// src/core/wavelet.hpp:55-58):
+// Both layouts replace the reference's two-level super/sub-block directory
+// (/root/reference/src/core/bitvector.hpp:94-99) and its 8 std::vector-backed levels
+// (src/core/wavelet.hpp:55-58). Symbols are first recoded to compact codes 0..sigma-1 (order
+// preserving), B = ceil(log2 sigma) bits.
 //
-//   level l of the wavelet matrix = nblk lines of 64 bytes, line b = 16 x u32:
-//       word 0      : rank1 of the level before bit 480*b   (absolute, n < 2^32)
-//       words 1..15 : bits [480*b, 480*b+480) of the level, LSB-first inside each word
-//   nblk = n/480 + 1, so position p == n (ep starts at n) always has a line; bits past n are 0.
-//   rank1_l(p) = line[p/480].word0 + popcount(payload bits below p%480): ONE 64-byte line,
-//   fetched as 4 x 128-bit (or 2 x 256-bit) loads by a sub-warp — one sector pair in DRAM/L2.
+// LAYOUT 2 (default) — "nibble levels", 128-byte lines.  ncu on B200 shows that every L2 miss
+// fills a whole 128-byte line from HBM and that random fetches top out at ~37 G lines/s whatever
+// their size (profiles/README.md), so the unit of the index is the 128-byte line and each line
+// resolves FOUR bits of the symbol instead of one:
+//   levels  = 1 if B <= 4 (DNA, protein-reduced alphabets), else 2 (bytes): level 0 holds the
+//             high part hi = code >> 4, level 1 the low nibbles lo = code & 15 stably grouped by
+//             hi (a 16-ary wavelet matrix: group g starts at start1[g] = #{codes with hi < g}).
+//   line b of a level = 128 symbols [128b, 128b+128) + 16 absolute counters, as 4 chunks of 32 B:
+//       chunk j : cnt[4j..4j+3] (u32: #symbols == v in the level before this line)
+//                 pay[4j..4j+3] (u32: symbols 32j..32j+31 of the line, 4 bits each, LSB first)
+//   rank_l(v,p) = line[p>>7].cnt[v] + #{k < (p&127) : sym[k] == v}: ONE line, fetched by a
+//   4-lane sub-warp as four 256-bit loads (one L1 wavefront, four sectors, one DRAM fetch).
+//   nblk = n/128 + 1 so that p == n (ep starts at n) has a line; padding symbols are 0 and are
+//   never counted (they lie at or beyond every queried offset).
+//   Backward search:  C[c] + occ(c,i) = base[c] + rank_last(lo, start1[hi] + rank_0(hi, i))
+//   with base[c] = C[c] - rank_1(lo, start1[hi]) = C[c] - #{codes with smaller hi and the same lo}.
+//
+// LAYOUT 1 — binary wavelet matrix, 64-byte lines (the north star's literal layout; kept
+// selectable with CSFM_BUILD_LAYOUT_BINARY64 for A/B measurements):
+//   level l = nblk lines of 64 bytes: word 0 = rank1 before bit 480*b, words 1..15 = 480 bits.
+//   path(c,i): p <- i; per level p <- bit ? zeros[l] + rank1_l(p) : p - rank1_l(p);
+//   C[c] + occ(c,i) = base[c] + path(c,i), base[c] = C[c] - path(c,0).
 //
 // rank(c,i) of the reference (wavelet.cpp:59-96) follows TWO positions (start,end) per level;
-// start always descends from 0, so it is a per-symbol constant:
-//   path(c,i)   : p <- i; for each level, p <- bit ? zeros[l] + rank1_l(p) : p - rank1_l(p)
-//   rank(c,i)   = path(c,i) - path(c,0)          (checked against the reference in tests)
-// and backward search needs  C[c] + rank(c,i) = base[c] + path(c,i),  base[c] = C[c]-path(c,0).
+// start always descends from 0, so it folds into the per-symbol constant base[c].
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace csfm {
 
+constexpr uint32_t kLayoutBinary64 = 1;
+constexpr uint32_t kLayoutNibble128 = 2;
+
+// layout 1
 constexpr uint32_t kPayloadBits = 480;  // bits per 64-byte line
 constexpr uint32_t kLineBytes = 64;
+// layout 2
+constexpr uint32_t kSymsPerLine = 128;  // 4-bit symbols per 128-byte line
+constexpr uint32_t kLine2Bytes = 128;
+
 constexpr uint32_t kMaxLevels = 8;
 constexpr uint64_t kMaxN = 0xFFFFFFFEull;  // n < 2^32 - 1 (reference: u32 SA/C, fm_index.hpp:43-44)
-constexpr uint32_t kAbsent = 0xFFFFFFFFu;
 
 // Fixed-size header at the start of the device blob (also the host/.csidx representation).
 struct BlobHeader {
   char magic[8];  // "CSFMDEV1"
   uint32_t version;
-  uint32_t levels;  // L
+  uint32_t levels;  // stored levels: layout 1: ceil(log2 sigma) or 8; layout 2: 1 or 2
   uint64_t n;
   uint32_t sigma;
   uint32_t stride;
   uint64_t nsamp;
   uint64_t nblk;          // lines per level
   uint64_t off_levels;    // byte offset of level 0
-  uint64_t level_stride;  // bytes between levels (nblk*64 rounded up to 256)
+  uint64_t level_stride;  // bytes between levels (multiple of 256)
   uint64_t off_ssa;       // byte offset of the SA samples (u32)
   uint64_t total_bytes;
-  uint32_t zeros[kMaxLevels];  // number of 0 bits per level
-  uint32_t reserved0[16];
+  uint32_t zeros[kMaxLevels];  // layout 1: number of 0 bits per level
+  uint32_t layout;             // kLayoutBinary64 | kLayoutNibble128
+  uint32_t code_bits;          // B
+  uint32_t reserved0[14];
+  uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
   uint32_t pad0[3];
-  uint32_t base_by_byte[256];  // C[b] - path(code(b),0)   (u32 wrap-around arithmetic)
+  uint32_t base_by_byte[256];  // see above (u32 wrap-around arithmetic)
   uint32_t base_by_code[256];  // same, indexed by compact code (LF step)
   uint8_t code_of_byte[256];   // compact code, 0 for absent bytes (absence <=> C[b+1]==C[b])
   uint8_t byte_of_code[256];
@@ -66,6 +90,8 @@ struct IndexView {
   uint32_t L;
   uint32_t stride;
   uint32_t nsamp;
+  uint32_t layout;
+  uint32_t pad;
   uint32_t zeros[kMaxLevels];
 };
 
@@ -80,15 +106,26 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
-// mask of the low x bits, x clamped to [0,32]
-__device__ __forceinline__ uint32_t low_mask(int x) {
-  // bmsk.clamp would do; shifts with clamping semantics are as cheap
-  return x <= 0 ? 0u : (x >= 32 ? 0xFFFFFFFFu : ((1u << x) - 1u));
+struct Chunk32 {  // one 32-byte chunk of a layout-2 line: 4 counters + 4 payload words
+  uint32_t c0, c1, c2, c3, p0, p1, p2, p3;
+};
+
+// 256-bit load (LDG.E.256 on sm_100a): one instruction per lane, one wavefront per 4-lane group.
+__device__ __forceinline__ Chunk32 ldg_nc_v8(const void* p) {
+  Chunk32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.c0), "=r"(r.c1), "=r"(r.c2), "=r"(r.c3), "=r"(r.p0), "=r"(r.p1), "=r"(r.p2), "=r"(r.p3)
+               : "l"(p));
+  return r;
 }
 
-// Partial rank of one lane of a 4-lane group. `w` = the lane's 16 bytes of the line (words
-// 4j..4j+3), `off` = p % 480. Lane 0's word 0 is the absolute counter and is added as a value.
-// Summing the four partials gives rank1(p).
+// mask of the low x bits, x clamped to [0,32]:  high word of (0x00000000FFFFFFFF << min(x,32))
+__device__ __forceinline__ uint32_t low_mask(int x) {
+  return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(x, 0));
+}
+
+// layout 1: partial rank of one lane of a 4-lane group. `w` = the lane's 16 bytes of the line
+// (words 4j..4j+3), `off` = p % 480. Lane 0's word 0 is the absolute counter (added as a value).
 __device__ __forceinline__ uint32_t lane_partial_rank(uint4 w, uint32_t off, int j) {
   // line word k covers payload bits [32(k-1), 32k): bits below off => x = off - 32(k-1)
   const int x0 = (int)off - 32 * (4 * j - 1);
@@ -96,6 +133,30 @@ __device__ __forceinline__ uint32_t lane_partial_rank(uint4 w, uint32_t off, int
   r += __popc(w.y & low_mask(x0 - 32));
   r += __popc(w.z & low_mask(x0 - 64));
   r += __popc(w.w & low_mask(x0 - 96));
+  return r;
+}
+
+// layout 2: number of 4-bit fields of `w` equal to the nibble replicated in `pat`, among the
+// lowest `nsym` fields (nsym clamped to [0,8]).
+__device__ __forceinline__ uint32_t nibble_matches(uint32_t w, uint32_t pat, int nsym) {
+  const uint32_t x = w ^ pat;                                        // zero nibble <=> match
+  const uint32_t nz = ((x & 0x77777777u) + 0x77777777u) | x;         // bit 3 of a nibble set <=> nibble != 0
+  const uint32_t hit = ~nz & 0x88888888u & low_mask(4 * nsym);
+  return (uint32_t)__popc(hit);
+}
+
+// layout 2: partial rank of lane j (0..3) of a group: its chunk holds cnt[4j..4j+3] and the
+// symbols 32j..32j+31 of the line. v = nibble to count, pat = v * 0x11111111, off = p & 127.
+__device__ __forceinline__ uint32_t lane_partial_rank2(const Chunk32& k, uint32_t v, uint32_t pat, uint32_t off,
+                                                       int j) {
+  const uint32_t comp = v & 3u;
+  const uint32_t cnt = comp == 0 ? k.c0 : comp == 1 ? k.c1 : comp == 2 ? k.c2 : k.c3;
+  uint32_t r = ((v >> 2) == (uint32_t)j) ? cnt : 0u;
+  const int s0 = (int)off - 32 * j;  // symbols of this chunk that lie below off
+  r += nibble_matches(k.p0, pat, s0);
+  r += nibble_matches(k.p1, pat, s0 - 8);
+  r += nibble_matches(k.p2, pat, s0 - 16);
+  r += nibble_matches(k.p3, pat, s0 - 24);
   return r;
 }
 

@@ -1,0 +1,97 @@
+// csfm_kernels.cuh — pieces shared by the query kernels of both layouts: the per-CTA table
+// copy, the warp-local work queue and the kernel argument blocks.
+#pragma once
+#include "csfm_common.cuh"
+
+namespace csfm {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kChunk = 32;  // queries fetched per warp per global atomic
+
+struct Tables {  // per-CTA shared-memory copy of the byte-indexed tables
+  uint32_t C[257];
+  uint32_t pad[3];
+  uint32_t base_by_byte[256];
+  uint32_t base_by_code[256];
+  uint32_t start1[16];
+  uint8_t code_of_byte[256];
+  uint8_t byte_of_code[256];
+};
+
+__device__ __forceinline__ void load_tables(Tables& t, const BlobHeader* __restrict__ h) {
+  for (int i = threadIdx.x; i < 257; i += blockDim.x) t.C[i] = h->C[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    t.base_by_byte[i] = h->base_by_byte[i];
+    t.base_by_code[i] = h->base_by_code[i];
+    t.code_of_byte[i] = h->code_of_byte[i];
+    t.byte_of_code[i] = h->byte_of_code[i];
+  }
+  if (threadIdx.x < 16) t.start1[threadIdx.x] = h->start1[threadIdx.x];
+  __syncthreads();
+}
+
+// Warp-local work queue over [0,total): returns this sub-warp's next item or ~0ull.
+struct WarpQueue {
+  unsigned long long next = 0, end = 0;
+  bool exhausted = false;
+};
+
+// Called by all 32 lanes (converged). `need` = this sub-warp wants an item. Returns the item
+// index or ~0ull. A partially served round simply leaves some sub-warps idle for one trip.
+__device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need, int lane,
+                                                         unsigned long long* cursor,
+                                                         unsigned long long total) {
+  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & 0x11111111u;  // leaders
+  if (need_mask == 0) return ~0ull;
+  if (q.next >= q.end && !q.exhausted) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) {
+      q.exhausted = true;
+    } else {
+      q.next = base;
+      q.end = (base + kChunk < total) ? base + kChunk : total;
+    }
+  }
+  const unsigned long long avail = q.end - q.next;
+  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
+  const unsigned cnt = __popc(need_mask);
+  unsigned long long item = ~0ull;
+  if (need && my_rank < avail) item = q.next + my_rank;
+  q.next += (cnt < avail) ? cnt : avail;
+  return item;
+}
+
+struct CountArgs {
+  const uint8_t* bytes;
+  const uint64_t* offs;
+  unsigned long long npat;
+  uint64_t* counts;    // nullable
+  uint64_t* sp_ep;     // nullable, 2 per query
+  uint32_t* row_sp;    // nullable (locate pass 1)
+  uint32_t* row_cnt;   // nullable (locate pass 1): min(count, limit), 0 for empty patterns
+  uint32_t limit32;
+  unsigned long long* cursor;
+  unsigned long long* steps_total;  // nullable (instrumentation)
+};
+
+struct WalkArgs {
+  uint64_t* out_pos;  // in: SA row, out: text position
+  unsigned long long total;
+  const uint64_t* out_offs;  // npat+1 (to attribute a failed walk to its query)
+  unsigned long long npat;
+  int32_t* status;
+  unsigned long long* cursor;
+  unsigned long long* lf_total;  // nullable
+};
+
+// Layout-2 kernels (csfm_query2.cu); launched by the dispatchers in csfm_query.cu.
+void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream);
+void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
+void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
+int max_blocks_per_sm_count2();
+int max_blocks_per_sm_walk2();
+int max_blocks_per_sm_access2();
+
+}  // namespace csfm

@@ -17,83 +17,15 @@
 #include <cub/device/device_scan.cuh>
 
 #include "csfm_host.hpp"
+#include "csfm_kernels.cuh"
 
 namespace csfm {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr uint32_t kChunk = 32;  // queries fetched per warp per global atomic
-
-struct Tables {  // per-CTA shared-memory copy of the byte-indexed tables
-  uint32_t C[257];
-  uint32_t pad[3];
-  uint32_t base_by_byte[256];
-  uint32_t base_by_code[256];
-  uint8_t code_of_byte[256];
-  uint8_t byte_of_code[256];
-};
-
-__device__ __forceinline__ void load_tables(Tables& t, const BlobHeader* __restrict__ h) {
-  for (int i = threadIdx.x; i < 257; i += blockDim.x) t.C[i] = h->C[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    t.base_by_byte[i] = h->base_by_byte[i];
-    t.base_by_code[i] = h->base_by_code[i];
-    t.code_of_byte[i] = h->code_of_byte[i];
-    t.byte_of_code[i] = h->byte_of_code[i];
-  }
-  __syncthreads();
-}
-
-// Warp-local work queue over [0,total): returns this sub-warp's next item or ~0ull.
-struct WarpQueue {
-  unsigned long long next = 0, end = 0;
-  bool exhausted = false;
-};
-
-// Called by all 32 lanes (converged). `need` = this sub-warp wants an item. Returns the item
-// index or ~0ull. A partially served round simply leaves some sub-warps idle for one trip.
-__device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need, int lane,
-                                                         unsigned long long* cursor,
-                                                         unsigned long long total) {
-  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & 0x11111111u;  // leaders
-  if (need_mask == 0) return ~0ull;
-  if (q.next >= q.end && !q.exhausted) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= total) {
-      q.exhausted = true;
-    } else {
-      q.next = base;
-      q.end = (base + kChunk < total) ? base + kChunk : total;
-    }
-  }
-  const unsigned long long avail = q.end - q.next;
-  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
-  const unsigned cnt = __popc(need_mask);
-  unsigned long long item = ~0ull;
-  if (need && my_rank < avail) item = q.next + my_rank;
-  q.next += (cnt < avail) ? cnt : avail;
-  return item;
-}
-
 // ------------------------------------------------------------------------------------------
-// count: backward search (fm_index.cpp:79-101)
+// count: backward search (fm_index.cpp:79-101), layout 1
 // ------------------------------------------------------------------------------------------
-struct CountArgs {
-  const uint8_t* bytes;
-  const uint64_t* offs;
-  unsigned long long npat;
-  uint64_t* counts;    // nullable
-  uint64_t* sp_ep;     // nullable, 2 per query
-  uint32_t* row_sp;    // nullable (locate pass 1)
-  uint32_t* row_cnt;   // nullable (locate pass 1): min(count, limit), 0 for empty patterns
-  uint32_t limit32;
-  unsigned long long* cursor;
-  unsigned long long* steps_total;  // nullable (instrumentation)
-};
-
 __global__ void __launch_bounds__(kThreads, 6)
 count_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
@@ -229,16 +161,6 @@ __global__ void expand_rows_kernel(const uint32_t* __restrict__ row_sp,
     for (uint64_t k = lane; k < o1 - o0; k += 32) out_pos[o0 + k] = sp + k;
   }
 }
-
-struct WalkArgs {
-  uint64_t* out_pos;  // in: SA row, out: text position
-  unsigned long long total;
-  const uint64_t* out_offs;  // npat+1 (to attribute a failed walk to its query)
-  unsigned long long npat;
-  int32_t* status;
-  unsigned long long* cursor;
-  unsigned long long* lf_total;  // nullable
-};
 
 __global__ void __launch_bounds__(kThreads, 6)
 walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
@@ -405,12 +327,16 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   a.limit32 = limit > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)limit;
   a.cursor = ctr;
   a.steps_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
-  const int grid_max = persistent_grid(idx, (const void*)count_kernel);
+  const bool nib = idx->view.layout == kLayoutNibble128;
+  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2() : persistent_grid(idx, (const void*)count_kernel);
   const uint64_t want = (npat * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-  count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
+  if (nib)
+    launch_count2(idx->view, a, grid, stream);
+  else
+    count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
   CSFM_CUDA(cudaGetLastError());
   idx->stats.kernel_launches += 1;
@@ -477,12 +403,16 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   w.status = d_status;
   w.cursor = ctr;
   w.lf_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
-  const int grid_max = persistent_grid(idx, (const void*)walk_kernel);
+  const bool nib = idx->view.layout == kLayoutNibble128;
+  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
   const uint64_t want = (total * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-  walk_kernel<<<grid, kThreads, 0, stream>>>(idx->view, w);
+  if (nib)
+    launch_walk2(idx->view, w, grid, stream);
+  else
+    walk_kernel<<<grid, kThreads, 0, stream>>>(idx->view, w);
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
   CSFM_CUDA(cudaGetLastError());
   idx->stats.kernel_launches += 2;
@@ -493,12 +423,19 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
 
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream) {
   if (idx->h.n == 0) return CSFM_OK;
+  const bool nib = idx->view.layout == kLayoutNibble128;
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, access_kernel, kThreads, 0);
+  if (nib)
+    per_sm = max_blocks_per_sm_access2();
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, access_kernel, kThreads, 0);
   if (per_sm < 1) per_sm = 1;
   const uint64_t want = (idx->h.n * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)idx->num_sms * per_sm);
-  access_kernel<<<grid, kThreads, 0, stream>>>(idx->view, d_out);
+  if (nib)
+    launch_access2(idx->view, d_out, grid, stream);
+  else
+    access_kernel<<<grid, kThreads, 0, stream>>>(idx->view, d_out);
   CSFM_CUDA(cudaGetLastError());
   return CSFM_OK;
 }

@@ -1,0 +1,299 @@
+// csfm_query2.cu — query kernels for layout 2 (16-ary levels in 128-byte lines), sm_100a.
+//
+// Same execution model as csfm_query.cu (4-lane sub-warp per query, flat lock-step state machine,
+// warp-local refill) but every trip resolves FOUR bits of the symbol: a byte alphabet needs two
+// dependent line fetches per rank instead of eight, DNA one instead of three. One rank = one
+// 128-byte line = four 256-bit loads (LDG.E.256, one per lane, one L1 wavefront), a counter pick,
+// four nibble-match popcounts per lane and two xor-shuffles.
+//
+// Replaces cs::FMIndex::count / locate (/root/reference/src/api/fm_index.cpp:79-157),
+// cs::WaveletTree::rank / access (src/core/wavelet.cpp:59-128) and cs::BitVector::rank1
+// (src/core/bitvector.cpp:165-230).
+#include "csfm_host.hpp"
+#include "csfm_kernels.cuh"
+
+namespace csfm {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// count (fm_index.cpp:79-101)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 5)
+count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const bool two = iv.L == 2;
+  WarpQueue wq;
+
+  bool active = false;
+  unsigned long long q = 0;      // query index
+  const uint8_t* ptr = nullptr;  // address of the character being processed
+  uint32_t rem = 0;              // characters left including the current one
+  uint32_t sp_pos = 0, ep_pos = 0, base = 0, add0 = 0, code = 0, level = 0, next_byte = 0;
+  uint32_t my_steps = 0;
+
+  auto finish = [&](uint32_t cnt, uint32_t sp, uint32_t ep) {
+    if (j == 0) {
+      if (a.counts) a.counts[q] = cnt;
+      if (a.sp_ep) {
+        a.sp_ep[2 * q] = sp;
+        a.sp_ep[2 * q + 1] = ep;
+      }
+      if (a.row_sp) {
+        a.row_sp[q] = sp;
+        a.row_cnt[q] = cnt < a.limit32 ? cnt : a.limit32;
+      }
+    }
+    active = false;
+  };
+  auto begin_step = [&](uint32_t b, uint32_t sp, uint32_t ep) {
+    ++my_steps;
+    if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
+      finish(0, 0, 0);
+      return;
+    }
+    code = tb.code_of_byte[b];
+    base = tb.base_by_byte[b];
+    add0 = tb.start1[code >> 4];
+    sp_pos = sp;
+    ep_pos = ep;
+    level = 0;
+    if (rem > 1) next_byte = ptr[-1];  // prefetch: in flight during the rank levels
+  };
+
+  for (;;) {
+    // ---- refill -----------------------------------------------------------------------
+    const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.npat);
+    if (item != ~0ull) {
+      q = item;
+      const uint64_t o0 = a.offs[q], o1 = a.offs[q + 1];
+      const uint64_t m = o1 - o0;
+      active = true;
+      if (m == 0) {
+        // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
+        if (j == 0) {
+          if (a.counts) a.counts[q] = iv.n;
+          if (a.sp_ep) { a.sp_ep[2 * q] = 0; a.sp_ep[2 * q + 1] = 0; }
+          if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
+        }
+        active = false;
+      } else {
+        // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
+        const uint32_t b = a.bytes[o1 - 1];
+        const uint32_t sp = tb.C[b], ep = tb.C[b + 1];
+        ++my_steps;
+        if (sp >= ep) {
+          finish(0, 0, 0);
+        } else if (m == 1) {
+          finish(ep - sp, sp, ep);
+        } else {
+          rem = (uint32_t)(m - 1);
+          ptr = a.bytes + (o1 - 2);
+          begin_step(*ptr, sp, ep);
+        }
+      }
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+
+    // ---- one 16-ary level for the two interval ends -------------------------------------
+    const bool last = !two || level == 1;
+    const uint32_t v = (two && level == 0) ? (code >> 4) : (code & 15u);
+    const uint32_t pat = v * 0x11111111u;
+    Chunk32 ks = {0, 0, 0, 0, 0, 0, 0, 0}, ke = ks;
+    const uint32_t os = sp_pos & (kSymsPerLine - 1), oe = ep_pos & (kSymsPerLine - 1);
+    if (active) {
+      const uint8_t* lv = iv.levels + (uint64_t)level * iv.level_stride + j * 32;
+      const uint32_t bs = sp_pos >> 7, be = ep_pos >> 7;
+      ks = ldg_nc_v8(lv + (uint64_t)bs * kLine2Bytes);
+      ke = (be == bs) ? ks : ldg_nc_v8(lv + (uint64_t)be * kLine2Bytes);
+    }
+    const uint32_t rs = group4_sum(lane_partial_rank2(ks, v, pat, os, j));
+    const uint32_t re = group4_sum(lane_partial_rank2(ke, v, pat, oe, j));
+    if (active) {
+      const uint32_t add = last ? base : add0;
+      sp_pos = add + rs;
+      ep_pos = add + re;
+      level = 1;
+      if (last) {
+        const uint32_t sp = sp_pos, ep = ep_pos;  // fm_index.cpp:92-93
+        if (sp >= ep) {
+          finish(0, 0, 0);
+        } else if (--rem == 0) {
+          finish(ep - sp, sp, ep);
+        } else {
+          --ptr;
+          begin_step(next_byte, sp, ep);
+        }
+      }
+    }
+  }
+  if (a.steps_total) {
+    unsigned s = (j == 0) ? my_steps : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
+  }
+}
+
+// One level of access(p) fused with rank (both read the same line): returns the nibble at p in
+// `v` and rank_l(v, p) as the function value. All 32 lanes must call it (shuffles).
+__device__ __forceinline__ uint32_t access_rank_level(const IndexView& iv, uint32_t level, uint32_t p, bool active,
+                                                      int lane, int j, uint32_t& v) {
+  Chunk32 k = {0, 0, 0, 0, 0, 0, 0, 0};
+  const uint32_t off = p & (kSymsPerLine - 1);
+  if (active)
+    k = ldg_nc_v8(iv.levels + (uint64_t)level * iv.level_stride + (uint64_t)(p >> 7) * kLine2Bytes + j * 32);
+  const uint32_t w = off >> 3;  // payload word holding symbol `off`: lane w>>2, component w&3
+  const uint32_t comp = w & 3u;
+  const uint32_t mine = comp == 0 ? k.p0 : comp == 1 ? k.p1 : comp == 2 ? k.p2 : k.p3;
+  const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, mine, (lane & ~3) | (int)(w >> 2));
+  v = (wsel >> (4 * (off & 7u))) & 15u;
+  return group4_sum(lane_partial_rank2(k, v, v * 0x11111111u, off, j));
+}
+
+// ------------------------------------------------------------------------------------------
+// locate: rows -> text positions (fm_index.cpp:125-153, LF of fm_index.hpp:62-66)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 5)
+walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const bool two = iv.L == 2;
+  WarpQueue wq;
+
+  bool active = false;
+  unsigned long long slot = 0;
+  uint32_t start = 0, p = 0, steps = 0, hi = 0, level = 0;
+  uint32_t my_lf = 0;
+
+  // Where the reference throws, the whole query fails: attribute the slot to its query.
+  auto fail_walk = [&](int why) {
+    if (j == 0) {
+      unsigned long long lo = 0, hi_q = a.npat;  // last q with out_offs[q] <= slot
+      while (hi_q - lo > 1) {
+        const unsigned long long mid = (lo + hi_q) >> 1;
+        if (a.out_offs[mid] <= slot) lo = mid; else hi_q = mid;
+      }
+      if (a.status) atomicMax(&a.status[lo], why);
+      a.out_pos[slot] = 0;
+    }
+    active = false;
+  };
+  auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]
+    const uint32_t k = row / iv.stride;
+    if (k >= iv.nsamp) {  // fm_index.cpp:141-146 (unreachable for a consistent index)
+      fail_walk((int)CSFM_Q_SSA_OOB);
+      return;
+    }
+    if (j == 0) {
+      uint64_t pos = (uint64_t)iv.ssa[k] + steps;  // fm_index.cpp:147-152
+      if (pos >= iv.n) pos -= iv.n;                // sa_val < n and steps < n
+      a.out_pos[slot] = pos;
+    }
+    active = false;
+  };
+
+  for (;;) {
+    const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
+    if (item != ~0ull) {
+      slot = item;
+      start = (uint32_t)a.out_pos[slot];
+      steps = 0;
+      active = true;
+      if (start % iv.stride == 0) {
+        emit(start);
+      } else {
+        p = start;
+        level = 0;
+      }
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+
+    uint32_t v;
+    const uint32_t r = access_rank_level(iv, level, p, active, lane, j, v);
+    if (active) {
+      if (two && level == 0) {
+        hi = v;
+        p = tb.start1[v] + r;
+        level = 1;
+      } else {
+        // LF(i) = C[c] + occ(c,i) = base[c] + rank_last(lo, .)   (fm_index.hpp:62-66)
+        const uint32_t code = two ? ((hi << 4) | v) : v;
+        const uint32_t row = tb.base_by_code[code] + r;
+        ++steps;
+        ++my_lf;
+        if (row % iv.stride == 0) {
+          emit(row);
+        } else if (row == start || steps >= iv.n) {
+          // LF is a permutation: back at the start without meeting a sampled row means the
+          // reference would walk n steps and throw (fm_index.cpp:130-138).
+          fail_walk((int)CSFM_Q_LF_WALK_EXCEEDED);
+        } else {
+          p = row;
+          level = 0;
+        }
+      }
+    }
+  }
+  if (a.lf_total) {
+    unsigned s = (j == 0) ? my_lf : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0 && s) atomicAdd(a.lf_total, (unsigned long long)s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// access: BWT[i] for all i (wavelet.cpp:102-128) — verification / export, not a query path
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+access2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const bool two = iv.L == 2;
+  const uint64_t group = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 2;
+  const uint64_t trips = ((uint64_t)iv.n + ngroups - 1) / ngroups;
+  for (uint64_t t = 0; t < trips; ++t) {
+    const uint64_t i = t * ngroups + group;
+    const bool valid = i < iv.n;
+    uint32_t v;
+    uint32_t r = access_rank_level(iv, 0, valid ? (uint32_t)i : 0u, valid, lane, j, v);
+    uint32_t code = v;
+    if (two) {
+      const uint32_t hi = v;
+      r = access_rank_level(iv, 1, tb.start1[hi] + r, valid, lane, j, v);
+      code = (hi << 4) | v;
+    }
+    if (valid && j == 0) out[i] = tb.byte_of_code[code];
+  }
+}
+
+int blocks_per_sm(const void* kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm;
+}
+
+}  // namespace
+
+void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream) {
+  count2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+}
+void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
+  walk2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+}
+void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
+  access2_kernel<<<grid, kThreads, 0, stream>>>(iv, out);
+}
+int max_blocks_per_sm_count2() { return blocks_per_sm((const void*)count2_kernel); }
+int max_blocks_per_sm_walk2() { return blocks_per_sm((const void*)walk2_kernel); }
+int max_blocks_per_sm_access2() { return blocks_per_sm((const void*)access2_kernel); }
+
+}  // namespace csfm

@@ -67,19 +67,25 @@ typedef struct {
 
 /* Build flags. */
 #define CSFM_BUILD_DEFAULT 0u
-#define CSFM_BUILD_NO_COMPACT 1u /* keep all 8 wavelet levels even if the text uses < 129 symbols */
+#define CSFM_BUILD_NO_COMPACT 1u /* index raw byte values (8 bits) even if the text uses few symbols */
 #define CSFM_BUILD_KEEP_SA 2u    /* keep the full suffix array on the device for csfm_get_sa */
+#define CSFM_BUILD_LAYOUT_BINARY64 4u /* layout 1: binary wavelet matrix in 64-byte lines (one bit
+                                         per line fetch) instead of the default layout 2: 16-ary
+                                         levels in 128-byte lines (four bits per line fetch) */
 
 typedef struct {
   uint64_t n;          /* text length (cs::IndexMeta::n, fm_index.hpp:15) */
   uint32_t sigma;      /* distinct byte values present in the text */
-  uint32_t levels;     /* wavelet-matrix levels stored (8, or ceil(log2 sigma) when compacted) */
+  uint32_t levels;     /* levels stored = dependent line fetches per rank: layout 2: 1 (sigma <= 16)
+                          or 2; layout 1: ceil(log2 sigma), or 8 with CSFM_BUILD_NO_COMPACT */
   uint32_t ssa_stride; /* SA sample stride (cs::SSA::stride) */
   uint32_t device;     /* CUDA device ordinal */
   uint64_t nsamp;      /* number of SA samples = ceil(n / stride) */
   uint64_t blocks_per_level; /* 64-byte lines per level */
   uint64_t blob_bytes; /* size of the device-resident index */
   uint32_t has_sa;     /* full SA still resident (CSFM_BUILD_KEEP_SA) */
+  uint32_t layout;     /* 1 = binary / 64-byte lines, 2 = 16-ary / 128-byte lines */
+  uint32_t line_bytes; /* bytes fetched per rank per level: 64 or 128 */
   uint32_t reserved;
 } csfm_index_info;
 

@@ -50,14 +50,15 @@ def _check_queries(fm, idx, case):
 
 
 @pytest.mark.parametrize("case", FM["cases"], ids=[c["name"] for c in FM["cases"]])
-@pytest.mark.parametrize("flags", [0, 1], ids=["compact", "8levels"])
+@pytest.mark.parametrize("flags", [0, 1, 4, 5], ids=["nib128", "nib128-rawbytes", "bin64", "bin64-8levels"])
 def test_golden_from_text(fm, case, flags):
     """build_from_text on the GPU (SA -> BWT -> C -> wavelet -> SSA) + queries vs the reference."""
     text = bytes.fromhex(case["text_hex"])
     idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=case["stride"]), flags=flags | fm.BUILD_KEEP_SA)
     info = idx.info()
     assert info.n == case["n"]
-    assert info.levels == 8 or flags == 0
+    assert info.layout == (1 if flags & 4 else 2) and info.line_bytes == (64 if flags & 4 else 128)
+    assert info.levels == {0: info.levels, 1: 2, 4: info.levels, 5: 8}[flags] and 1 <= info.levels <= 8
     assert idx.C_array().tolist() == case["C"]
     assert idx.ssa().tolist() == case["ssa"]
     assert idx.bwt().tobytes() == bytes.fromhex(case["bwt_hex"])
@@ -126,12 +127,16 @@ def _mixed_patterns(rng, text, alpha, k, maxlen):
     return pats
 
 
+@pytest.mark.parametrize("layout", [0, 4], ids=["nib128", "bin64"])
 @pytest.mark.parametrize("sigma,n,stride,term,flags", [
     (2, 50_000, 4, True, 0), (4, 200_000, 32, True, 0), (4, 200_000, 32, True, 1), (5, 100_000, 7, False, 0),
+    (15, 90_000, 5, True, 0), (16, 90_000, 5, False, 0), (17, 90_000, 5, True, 0),
     (21, 150_000, 16, True, 0), (97, 120_000, 32, True, 0), (256, 300_000, 32, True, 0), (256, 65_537, 1, False, 0),
     (1, 5_000, 3, True, 0), (3, 479, 2, True, 0), (3, 480, 2, True, 0), (3, 481, 2, False, 0), (3, 961, 5, True, 0),
+    (3, 127, 2, True, 0), (3, 128, 2, False, 0), (3, 129, 2, True, 0), (40, 255, 3, True, 0), (40, 256, 3, False, 0),
 ])
-def test_random_vs_oracle(fm, sigma, n, stride, term, flags):
+def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
+    flags |= layout
     rng = np.random.default_rng(1000 * sigma + n + stride)
     text, alpha = _rand_text(rng, n, sigma, term)
     idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=flags | fm.BUILD_KEEP_SA)
