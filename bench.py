@@ -278,23 +278,10 @@ def run_engine(args, rank, world, local_rank):
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
     if world > 1:
-        nbytes_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            ptr, nbytes = idx.blob()
-            nbytes_t[0] = nbytes
-        dist.broadcast(nbytes_t, 0)
-        nbytes = int(nbytes_t.item())
-        blob_t = torch.as_tensor(_DevMem(ptr, nbytes), device=dev) if rank == 0 else torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        torch.cuda.synchronize()
+        # warm NCCL up on a small tensor so that bcast_ms measures the transfer, not communicator setup
+        dist.all_reduce(torch.zeros(1, device=dev))
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(blob_t, 0)  # the one ncclBroadcast of the path
-        e1.record()
-        torch.cuda.synchronize()
-        bcast_ms = e0.elapsed_time(e1)
-        if rank != 0:
-            idx = fm.FMIndex.attach_blob(blob_t.data_ptr(), nbytes, local_rank, keepalive=blob_t)
+        idx, bcast_ms = fm.parallel.replicate_index(idx if rank == 0 else None, dev, src=0)  # the one ncclBroadcast
     info = idx.info()
     L = int(info.levels)
     log(f"[rank {rank}] n={n} levels={L} sigma={info.sigma} blob={info.blob_bytes/1e6:.1f} MB text_gen={t_text:.2f}s "
@@ -457,8 +444,8 @@ def run_engine(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--n-log2", type=int, default=None, help="override text size (reduced sizes are flagged in config)")

@@ -18,4 +18,5 @@ if _NAME not in sys.modules:
 _mod = sys.modules[_NAME]
 globals().update({k: getattr(_mod, k) for k in dir(_mod) if not k.startswith("__")})
 workloads = importlib.import_module(_NAME + ".workloads")
+parallel = importlib.import_module(_NAME + ".parallel")
 PACKAGE_DIR = _PKG_DIR
