@@ -1,0 +1,13 @@
+#!/usr/bin/env bash
+# Builds libcs_b200.so: the C++ drop-in for the reference's static library `cs`
+# (cs::FMIndex over the C ABI of ../libcsfm.so). Plain g++, no CUDA headers needed.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/libcs_b200.so"
+CXX=/usr/bin/g++
+[[ -x "$CXX" ]] || CXX=g++
+if [[ -f "$OUT" && "$OUT" -nt "$HERE/src/api/fm_index.cpp" && "$OUT" -nt "$HERE/src/api/fm_index.hpp" && "$OUT" -nt "$HERE/../libcsfm.so" && "${1:-}" != "-f" ]]; then
+  exit 0
+fi
+"$CXX" -std=c++20 -O2 -fPIC -Wall -Wextra -shared -o "$OUT" "$HERE/src/api/fm_index.cpp" \
+  -L"$HERE/.." -lcsfm -Wl,-rpath,'$ORIGIN/..'

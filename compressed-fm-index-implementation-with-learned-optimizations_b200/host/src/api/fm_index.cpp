@@ -1,0 +1,141 @@
+// host/src/api/fm_index.cpp — cs::FMIndex over the C ABI of libcsfm.so (include/csfm.h).
+// Mirrors the behaviour of /root/reference/src/api/fm_index.cpp; contains no FM-index algorithm.
+#include "fm_index.hpp"
+
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "../../../../include/csfm.h"
+#include "../util/timer.hpp"
+
+namespace cs {
+
+namespace {
+
+int g_default_device = -1;
+
+int default_device() {
+  if (g_default_device >= 0) return g_default_device;
+  if (const char* e = std::getenv("CS_DEVICE")) return std::atoi(e);
+  return 0;
+}
+
+[[noreturn]] void throw_last(const char* what) {
+  throw std::runtime_error(std::string(what) + ": " + csfm_last_error());
+}
+
+void pack(const std::vector<std::string_view>& pats, std::vector<uint8_t>& bytes, std::vector<uint64_t>& offs) {
+  offs.resize(pats.size() + 1);
+  uint64_t total = 0;
+  for (size_t i = 0; i < pats.size(); ++i) {
+    offs[i] = total;
+    total += pats[i].size();
+  }
+  offs[pats.size()] = total;
+  bytes.resize(total ? total : 1);
+  for (size_t i = 0; i < pats.size(); ++i)
+    if (!pats[i].empty()) std::memcpy(bytes.data() + offs[i], pats[i].data(), pats[i].size());
+}
+
+}  // namespace
+
+void FMIndex::set_default_device(int device) { g_default_device = device; }
+
+FMIndex FMIndex::build_from_text(const std::string& text, const BuildParams& p) {
+  FMIndex idx;
+  idx.meta_.n = text.size();
+  idx.text_ = std::make_shared<const std::string>(text);
+  csfm_params cp{p.S, p.s, p.ssa_stride, p.eps};
+  csfm_index* h = nullptr;
+  {
+    // The reference prints four [TIMER] lines here (fm_index.cpp:26,31,50,57); the whole build is
+    // one device pipeline now, reported as a single line when CS_TIMERS=1.
+    const bool timers = std::getenv("CS_TIMERS") != nullptr;
+    std::unique_ptr<ScopeTimer> t(timers ? new ScopeTimer("build_from_text(gpu)") : nullptr);
+    if (csfm_build_from_text(reinterpret_cast<const uint8_t*>(text.data()), text.size(), &cp, default_device(),
+                             CSFM_BUILD_DEFAULT, &h) != CSFM_OK)
+      throw_last("build_from_text");
+  }
+  idx.handle_ = std::shared_ptr<csfm_index>(h, [](csfm_index* x) { csfm_destroy(x); });
+  return idx;
+}
+
+FMIndex FMIndex::open_directory(const std::string&) {
+  throw std::runtime_error("on-disk open not implemented yet");  // fm_index.cpp:72
+}
+
+int FMIndex::device() const {
+  csfm_index_info info;
+  if (!handle_ || csfm_info(handle_.get(), &info) != CSFM_OK) return -1;
+  return static_cast<int>(info.device);
+}
+
+void FMIndex::count_batch(const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
+                          uint64_t* sp_ep) const {
+  if (!handle_) throw std::runtime_error("count_batch: index not built");
+  if (csfm_count_batch(handle_.get(), bytes, offs, npat, counts, sp_ep) != CSFM_OK) throw_last("count_batch");
+}
+
+std::vector<uint64_t> FMIndex::count_batch(const std::vector<std::string_view>& patterns) const {
+  std::vector<uint8_t> bytes;
+  std::vector<uint64_t> offs;
+  pack(patterns, bytes, offs);
+  std::vector<uint64_t> counts(patterns.size());
+  if (!patterns.empty()) count_batch(bytes.data(), offs.data(), patterns.size(), counts.data());
+  return counts;
+}
+
+std::vector<uint64_t> FMIndex::count_batch(const std::vector<std::string>& patterns) const {
+  std::vector<std::string_view> v(patterns.begin(), patterns.end());
+  return count_batch(v);
+}
+
+uint64_t FMIndex::count(std::string_view pattern) const {
+  if (pattern.empty()) return meta_.n;  // fm_index.cpp:80
+  if (meta_.n == 0) return 0;           // fm_index.cpp:81
+  const uint64_t offs[2] = {0, pattern.size()};
+  uint64_t c = 0;
+  count_batch(reinterpret_cast<const uint8_t*>(pattern.data()), offs, 1, &c);
+  return c;
+}
+
+LocateBatch FMIndex::locate_batch(const std::vector<std::string_view>& patterns, size_t limit) const {
+  if (!handle_) throw std::runtime_error("locate_batch: index not built");
+  LocateBatch r;
+  r.offsets.assign(patterns.size() + 1, 0);
+  r.status.assign(patterns.size(), 0);
+  if (patterns.empty()) return r;
+  std::vector<uint8_t> bytes;
+  std::vector<uint64_t> offs;
+  pack(patterns, bytes, offs);
+  uint64_t total = 0;
+  int rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(), nullptr,
+                             0, r.status.data(), &total);
+  if (rc != CSFM_OK) throw_last("locate_batch");
+  r.positions.resize(total);
+  if (total) {
+    rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
+                           r.positions.data(), total, r.status.data(), &total);
+    if (rc != CSFM_OK) throw_last("locate_batch");
+  }
+  return r;
+}
+
+std::vector<uint64_t> FMIndex::locate(std::string_view pattern, size_t limit) const {
+  if (pattern.empty() || meta_.n == 0) return {};  // fm_index.cpp:109
+  LocateBatch r = locate_batch({pattern}, limit);
+  if (r.status[0] == CSFM_Q_LF_WALK_EXCEEDED)
+    throw std::runtime_error("locate: LF walk exceeded text length");  // fm_index.cpp:137
+  if (r.status[0] == CSFM_Q_SSA_OOB)
+    throw std::runtime_error("locate: SSA sample index out of range");  // fm_index.cpp:143
+  return std::move(r.positions);
+}
+
+std::string FMIndex::extract(uint64_t p, uint64_t len) const {
+  if (!text_ || p >= text_->size()) return {};  // fm_index.cpp:164
+  len = len < text_->size() - p ? len : text_->size() - p;
+  return text_->substr(p, len);
+}
+
+}  // namespace cs

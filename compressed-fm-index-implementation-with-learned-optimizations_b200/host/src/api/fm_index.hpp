@@ -1,0 +1,72 @@
+#pragma once
+// host/src/api/fm_index.hpp — drop-in for the reference header of the same path
+// (/root/reference/src/api/fm_index.hpp:9-68): same namespace, same BuildParams / IndexMeta,
+// same public methods with the same observable results, so the reference's callers
+// (tools/*.cpp, tests/fm_search_tests.cpp, tests/simple_tests.cpp, tests/debug_fm.cpp) compile
+// and run unchanged. Underneath, every query is a CUDA kernel launch through the C ABI in
+// include/csfm.h (libcsfm.so); there is no CPU implementation behind this class.
+//
+// Added on top of the reference surface: count_batch / locate_batch (the batched entry points of
+// BASELINE.json's north star) and device selection.
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <vector>
+
+struct csfm_index;  // include/csfm.h
+
+namespace cs {
+
+struct BuildParams {  // fm_index.hpp:11-14; only ssa_stride is honoured, as in the reference
+  uint32_t S = 512, s = 64, ssa_stride = 32;
+  double eps = 1.0;
+};
+struct IndexMeta { uint64_t n = 0; uint32_t sigma = 256; };  // fm_index.hpp:15
+
+/// Result of FMIndex::locate_batch: positions of query q are
+/// positions[offsets[q] .. offsets[q+1]) in SA-row order; status[q] != 0 where the reference's
+/// locate() would have thrown (1 = "locate: LF walk exceeded text length").
+struct LocateBatch {
+  std::vector<uint64_t> offsets;
+  std::vector<uint64_t> positions;
+  std::vector<int32_t> status;
+};
+
+class FMIndex {
+public:
+  /// fm_index.cpp:16-69 — SA, BWT, C, rank structure and sampled SA, all built on the GPU.
+  static FMIndex build_from_text(const std::string& text, const BuildParams& p);
+  /// fm_index.cpp:71-73 — throws std::runtime_error("on-disk open not implemented yet").
+  static FMIndex open_directory(const std::string& dir);
+
+  /// fm_index.cpp:79-101.
+  uint64_t count(std::string_view pattern) const;
+  /// fm_index.cpp:107-157 — SA-row order; throws std::runtime_error where the reference does.
+  std::vector<uint64_t> locate(std::string_view pattern, size_t limit = 100000) const;
+  /// fm_index.cpp:163-167.
+  std::string extract(uint64_t pos, uint64_t len) const;
+
+  // ---- batched entry points (new) ---------------------------------------------------------
+  std::vector<uint64_t> count_batch(const std::vector<std::string_view>& patterns) const;
+  std::vector<uint64_t> count_batch(const std::vector<std::string>& patterns) const;
+  /// Packed form: `bytes` holds the patterns back to back, offs[npat+1] their starts.
+  void count_batch(const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
+                   uint64_t* sp_ep = nullptr) const;
+  LocateBatch locate_batch(const std::vector<std::string_view>& patterns, size_t limit = 100000) const;
+
+  // ---- introspection / placement ------------------------------------------------------------
+  uint64_t size() const { return meta_.n; }
+  int device() const;
+  csfm_index* handle() const { return handle_.get(); }
+  /// Device used by build_from_text (default 0, or $CS_DEVICE).
+  static void set_default_device(int device);
+
+private:
+  IndexMeta meta_;
+  std::shared_ptr<const std::string> text_;  // host copy for extract(), like FMIndex::text_
+  std::shared_ptr<csfm_index> handle_;       // device-resident index; copies share it (read-only)
+};
+
+}  // namespace cs
