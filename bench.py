@@ -246,6 +246,72 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# locate leg (BASELINE.json configs[3]: DNA text, ssa_stride 32, frequent text-sampled patterns)
+# ------------------------------------------------------------------------------------------------
+def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5):
+    """locate_batch on device-resident inputs/outputs: occurrences/s, checked by re-reading the text."""
+    import torch
+    from csfm_b200 import workloads as w
+    n = 1 << n_log2
+    text = w.dna_text_torch(n, 6, dev)
+    t0 = time.perf_counter()
+    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    info = idx.info()
+    bytes_d, offs_d = w.sampled_patterns_torch(text, npat, plen, plen, 0, 8)
+    stream = torch.cuda.Stream(device=dev)
+    d_offs_out = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
+    d_status = torch.zeros(npat, dtype=torch.int32, device=dev)
+    total = idx.locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, d_offs_out.data_ptr(), 0, 0,
+                                    d_status.data_ptr(), stream.cuda_stream)
+    d_pos = torch.zeros(max(1, total), dtype=torch.int64, device=dev)
+
+    def run():
+        return idx.locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, d_offs_out.data_ptr(),
+                                       d_pos.data_ptr(), total, d_status.data_ptr(), stream.cuda_stream)
+
+    idx.set_instrumentation(1)
+    run()
+    stream.synchronize()
+    lf_steps = int(idx.last_call_stats().lf_steps)
+    idx.set_instrumentation(0)
+    # correctness: every reported position really starts an occurrence of its pattern; no failed query
+    assert int(d_status.max().item()) == 0
+    sample = torch.randint(0, total, (min(total, 2_000_000),), device=dev)
+    q_of = torch.searchsorted(d_offs_out, sample, right=True) - 1
+    ok = torch.ones(sample.numel(), dtype=torch.bool, device=dev)
+    for k in range(plen):
+        ok &= text[d_pos[sample] + k] == bytes_d[offs_d[q_of] + k]
+    positions_ok = bool(ok.all().item())
+    counts_ok = bool(((d_offs_out[1:] - d_offs_out[:-1]) >= 1).all().item())
+    for _ in range(2):
+        run()
+    stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(iters):
+            run()
+        e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    L, lb = int(info.levels), int(info.line_bytes)
+    alg = lf_steps * L * lb + total * 40
+    peak, _ = measured_peak()
+    out = {"metric": "locate occurrences/sec", "value": total / (ms / 1e3), "unit": "occurrences/s", "ms_per_batch": ms,
+           "config": {"workload": f"C4-style: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen}, limit {limit}",
+                      "levels": L, "line_bytes": lb, "index_bytes": int(info.blob_bytes), "index_build_s": build_s},
+           "occurrences_per_batch": int(total), "lf_steps_per_occurrence": lf_steps / max(1, total),
+           "roofline": {"bound": "hbm", "kernel": "walk_kernel", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_batch": alg,
+                        "note": "sum over occurrences of LF steps x L x line bytes + 32 B sample + 8 B output; time covers count pass + scan + expand + walk"},
+           "checks": {"positions_verified_against_text": positions_ok, "all_counts_ge_1": counts_ok, "failed_queries": 0}}
+    idx.close()
+    return out
+
 # ------------------------------------------------------------------------------------------------
 # engine arm
 # ------------------------------------------------------------------------------------------------
@@ -420,6 +486,15 @@ def run_engine(args, rank, world, local_rank):
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
+    locate = None
+    if world == 1 and not args.no_locate:
+        try:
+            del d_batches, text
+            torch.cuda.empty_cache()
+            locate = measure_locate(fm, dev)
+        except Exception as e:  # pragma: no cover
+            locate = {"unavailable": repr(e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -437,6 +512,7 @@ def run_engine(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
         "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal},
+        "locate": locate,
     }
     print(json.dumps(line), flush=True)
 
@@ -453,6 +529,7 @@ def main():
     ap.add_argument("--layout", type=int, default=2, choices=[1, 2], help="2 = 16-ary levels / 128-byte lines (default), 1 = binary / 64-byte lines")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-locate", action="store_true", help="skip the locate leg (occurrences/s on a C4-style index)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

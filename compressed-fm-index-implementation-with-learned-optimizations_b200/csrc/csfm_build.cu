@@ -155,12 +155,12 @@ nib_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, int shift, uint8_t*
       // histogram: one shared add per distinct value per round
       const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? v : 0xFFu);
       if (valid && lane == __ffs(peers) - 1) hist[wib][v] += __popc(peers);
-      // 8 consecutive lanes -> one payload word
-      uint32_t x = v << (4 * (lane & 7));
-      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 1);
-      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 2);
+      // round r = chunk r; symbol s = lane of the chunk goes to word s&3, nibble s>>2
+      uint32_t x = v << (4 * (lane >> 2));
       x |= __shfl_xor_sync(0xFFFFFFFFu, x, 4);
-      if ((lane & 7) == 0) line[line_word_of_payload(4 * r + (lane >> 3))] = x;
+      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 8);
+      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 16);
+      if (lane < 4) line[line_word_of_payload(4 * r + lane)] = x;
       __syncwarp();
     }
     if (lane < 16) linecnt[(uint64_t)lane * nblk + b] = hist[wib][lane];

@@ -14,7 +14,9 @@
 //             hi (a 16-ary wavelet matrix: group g starts at start1[g] = #{codes with hi < g}).
 //   line b of a level = 128 symbols [128b, 128b+128) + 16 absolute counters, as 4 chunks of 32 B:
 //       chunk j : cnt[4j..4j+3] (u32: #symbols == v in the level before this line)
-//                 pay[4j..4j+3] (u32: symbols 32j..32j+31 of the line, 4 bits each, LSB first)
+//                 pay[4j..4j+3] (u32: symbols 32j..32j+31 of the line, 4 bits each, interleaved:
+//                                symbol s of the chunk sits in word s&3, nibble s>>2, so the four
+//                                per-word match masks fold into one hit word in symbol order)
 //   rank_l(v,p) = line[p>>7].cnt[v] + #{k < (p&127) : sym[k] == v}: ONE line, fetched by a
 //   4-lane sub-warp as four 256-bit loads (one L1 wavefront, four sectors, one DRAM fetch).
 //   nblk = n/128 + 1 so that p == n (ep starts at n) has a line; padding symbols are 0 and are
@@ -136,28 +138,33 @@ __device__ __forceinline__ uint32_t lane_partial_rank(uint4 w, uint32_t off, int
   return r;
 }
 
-// layout 2: number of 4-bit fields of `w` equal to the nibble replicated in `pat`, among the
-// lowest `nsym` fields (nsym clamped to [0,8]).
-__device__ __forceinline__ uint32_t nibble_matches(uint32_t w, uint32_t pat, int nsym) {
-  const uint32_t x = w ^ pat;                                        // zero nibble <=> match
-  const uint32_t nz = ((x & 0x77777777u) + 0x77777777u) | x;         // bit 3 of a nibble set <=> nibble != 0
-  const uint32_t hit = ~nz & 0x88888888u & low_mask(4 * nsym);
-  return (uint32_t)__popc(hit);
+// layout 2: symbol s (0..31) of a chunk lives in payload word s&3, nibble s>>2 (interleaved), so
+// that the four per-word match masks fold into ONE 32-bit hit word in symbol order:
+// bit s of chunk_hits() is set <=> symbol s of the chunk equals the nibble replicated in `pat`.
+__device__ __forceinline__ uint32_t nibble_eq_msb(uint32_t w, uint32_t pat) {
+  const uint32_t x = w ^ pat;                              // zero nibble <=> match
+  const uint32_t t = (x & 0x77777777u) + 0x77777777u;      // bit 3 set <=> low 3 bits != 0
+  return ~(t | x) & 0x88888888u;                           // bit 3 of every matching nibble
 }
-
-// layout 2: partial rank of lane j (0..3) of a group: its chunk holds cnt[4j..4j+3] and the
-// symbols 32j..32j+31 of the line. v = nibble to count, pat = v * 0x11111111, off = p & 127.
-__device__ __forceinline__ uint32_t lane_partial_rank2(const Chunk32& k, uint32_t v, uint32_t pat, uint32_t off,
-                                                       int j) {
+__device__ __forceinline__ uint32_t chunk_hits(const Chunk32& k, uint32_t pat) {
+  return (nibble_eq_msb(k.p0, pat) >> 3) | (nibble_eq_msb(k.p1, pat) >> 2) | (nibble_eq_msb(k.p2, pat) >> 1) |
+         nibble_eq_msb(k.p3, pat);
+}
+// cnt[v] if this lane's chunk holds it (lane j holds cnt[4j..4j+3]), else 0
+__device__ __forceinline__ uint32_t chunk_counter(const Chunk32& k, uint32_t v, int j) {
   const uint32_t comp = v & 3u;
   const uint32_t cnt = comp == 0 ? k.c0 : comp == 1 ? k.c1 : comp == 2 ? k.c2 : k.c3;
-  uint32_t r = ((v >> 2) == (uint32_t)j) ? cnt : 0u;
-  const int s0 = (int)off - 32 * j;  // symbols of this chunk that lie below off
-  r += nibble_matches(k.p0, pat, s0);
-  r += nibble_matches(k.p1, pat, s0 - 8);
-  r += nibble_matches(k.p2, pat, s0 - 16);
-  r += nibble_matches(k.p3, pat, s0 - 24);
-  return r;
+  return ((v >> 2) == (uint32_t)j) ? cnt : 0u;
+}
+// partial rank of lane j for offset off = p & 127, given the lane's counter share and hit word
+__device__ __forceinline__ uint32_t chunk_partial(uint32_t cnt, uint32_t hits, uint32_t off, int j) {
+  return cnt + (uint32_t)__popc(hits & low_mask((int)off - 32 * j));
+}
+// the symbol at offset off of a line, given this lane's chunk (valid in lane off>>5 only)
+__device__ __forceinline__ uint32_t chunk_symbol(const Chunk32& k, uint32_t off) {
+  const uint32_t s = off & 31u, comp = s & 3u;
+  const uint32_t w = comp == 0 ? k.p0 : comp == 1 ? k.p1 : comp == 2 ? k.p2 : k.p3;
+  return (w >> (4u * (s >> 2))) & 15u;
 }
 
 __device__ __forceinline__ uint32_t group4_sum(uint32_t v) {

@@ -1,10 +1,17 @@
 // csfm_query2.cu — query kernels for layout 2 (16-ary levels in 128-byte lines), sm_100a.
 //
-// Same execution model as csfm_query.cu (4-lane sub-warp per query, flat lock-step state machine,
-// warp-local refill) but every trip resolves FOUR bits of the symbol: a byte alphabet needs two
-// dependent line fetches per rank instead of eight, DNA one instead of three. One rank = one
-// 128-byte line = four 256-bit loads (LDG.E.256, one per lane, one L1 wavefront), a counter pick,
-// four nibble-match popcounts per lane and two xor-shuffles.
+// Execution model: a 4-lane sub-warp owns one query (count) / one occurrence row (locate). One
+// rank = one 128-byte line = four 256-bit loads (LDG.E.256, one per lane, ONE L1 wavefront), a
+// counter pick, one folded hit word + one masked popc per lane, two xor-shuffles. A byte
+// alphabet needs two dependent line fetches per rank, DNA one.
+//
+// All eight sub-warps of a warp run one loop in lock-step and in PHASE: a loop trip is a whole
+// backward-search step (level 0, level 1, step end), so the step-end code (interval test, next
+// pattern byte, table lookups) is issued once per step for the warp, not once per level per
+// straggler. A sub-warp that finishes refills at the next trip from a warp-local chunk of the
+// batch cursor (ballot-ranked, one global atomic per 32 queries). sp and ep usually fall in the
+// same line after ~4 steps: then one load and one hit word serve both ends, and the warp skips
+// the second hit computation altogether when no sub-warp needs it. Grids are persistent.
 //
 // Replaces cs::FMIndex::count / locate (/root/reference/src/api/fm_index.cpp:79-157),
 // cs::WaveletTree::rank / access (src/core/wavelet.cpp:59-128) and cs::BitVector::rank1
@@ -15,6 +22,29 @@
 namespace csfm {
 
 namespace {
+
+// rank_l(v, sp) and rank_l(v, ep) for one level. lv = level base + 32*j. All 32 lanes call it.
+__device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp_pos, uint32_t ep_pos,
+                                          bool active, int j, uint32_t& rs, uint32_t& re) {
+  const uint32_t pat = v * 0x11111111u;
+  const uint32_t ls = sp_pos & ~(kSymsPerLine - 1), le = ep_pos & ~(kSymsPerLine - 1);  // line*128 == byte offset
+  const uint32_t os = sp_pos - ls, oe = ep_pos - le;
+  const bool split = active && (le != ls);
+  Chunk32 ks = {0, 0, 0, 0, 0, 0, 0, 0}, ke = ks;
+  if (active) ks = ldg_nc_v8(lv + ls);
+  if (split) ke = ldg_nc_v8(lv + le);
+  const uint32_t hs = chunk_hits(ks, pat);
+  const uint32_t cs = chunk_counter(ks, v, j);
+  uint32_t he = hs, ce = cs;
+  if (__any_sync(0xFFFFFFFFu, split)) {  // warp-uniform: skipped once every interval is narrow
+    const uint32_t h2 = chunk_hits(ke, pat);
+    const uint32_t c2 = chunk_counter(ke, v, j);
+    he = split ? h2 : hs;
+    ce = split ? c2 : cs;
+  }
+  rs = group4_sum(chunk_partial(cs, hs, os, j));
+  re = group4_sum(chunk_partial(ce, he, oe, j));
+}
 
 // ------------------------------------------------------------------------------------------
 // count (fm_index.cpp:79-101)
@@ -27,30 +57,33 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const int lane = threadIdx.x & 31;
   const int j = lane & 3;
   const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv_last = lv0 + (two ? iv.level_stride : 0);
   WarpQueue wq;
 
   bool active = false;
   unsigned long long q = 0;      // query index
   const uint8_t* ptr = nullptr;  // address of the character being processed
   uint32_t rem = 0;              // characters left including the current one
-  uint32_t sp_pos = 0, ep_pos = 0, base = 0, add0 = 0, code = 0, level = 0, next_byte = 0;
+  uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
   uint32_t my_steps = 0;
 
-  auto finish = [&](uint32_t cnt, uint32_t sp, uint32_t ep) {
+  auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
     if (j == 0) {
       if (a.counts) a.counts[q] = cnt;
       if (a.sp_ep) {
-        a.sp_ep[2 * q] = sp;
-        a.sp_ep[2 * q + 1] = ep;
+        a.sp_ep[2 * q] = lo;
+        a.sp_ep[2 * q + 1] = hi;
       }
       if (a.row_sp) {
-        a.row_sp[q] = sp;
+        a.row_sp[q] = lo;
         a.row_cnt[q] = cnt < a.limit32 ? cnt : a.limit32;
       }
     }
     active = false;
   };
-  auto begin_step = [&](uint32_t b, uint32_t sp, uint32_t ep) {
+  // Sets up the step that prepends byte b to the interval [sp,ep).
+  auto begin_step = [&](uint32_t b) {
     ++my_steps;
     if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
       finish(0, 0, 0);
@@ -59,14 +92,11 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     code = tb.code_of_byte[b];
     base = tb.base_by_byte[b];
     add0 = tb.start1[code >> 4];
-    sp_pos = sp;
-    ep_pos = ep;
-    level = 0;
     if (rem > 1) next_byte = ptr[-1];  // prefetch: in flight during the rank levels
   };
 
   for (;;) {
-    // ---- refill -----------------------------------------------------------------------
+    // ---- refill (every sub-warp is at a step boundary here) -------------------------------
     const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.npat);
     if (item != ~0ull) {
       q = item;
@@ -84,7 +114,8 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
       } else {
         // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
         const uint32_t b = a.bytes[o1 - 1];
-        const uint32_t sp = tb.C[b], ep = tb.C[b + 1];
+        sp = tb.C[b];
+        ep = tb.C[b + 1];
         ++my_steps;
         if (sp >= ep) {
           finish(0, 0, 0);
@@ -93,41 +124,30 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         } else {
           rem = (uint32_t)(m - 1);
           ptr = a.bytes + (o1 - 2);
-          begin_step(*ptr, sp, ep);
+          begin_step(*ptr);
         }
       }
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
-    // ---- one 16-ary level for the two interval ends -------------------------------------
-    const bool last = !two || level == 1;
-    const uint32_t v = (two && level == 0) ? (code >> 4) : (code & 15u);
-    const uint32_t pat = v * 0x11111111u;
-    Chunk32 ks = {0, 0, 0, 0, 0, 0, 0, 0}, ke = ks;
-    const uint32_t os = sp_pos & (kSymsPerLine - 1), oe = ep_pos & (kSymsPerLine - 1);
-    if (active) {
-      const uint8_t* lv = iv.levels + (uint64_t)level * iv.level_stride + j * 32;
-      const uint32_t bs = sp_pos >> 7, be = ep_pos >> 7;
-      ks = ldg_nc_v8(lv + (uint64_t)bs * kLine2Bytes);
-      ke = (be == bs) ? ks : ldg_nc_v8(lv + (uint64_t)be * kLine2Bytes);
+    // ---- one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
+    uint32_t rs, re;
+    if (two) {
+      rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re);
+      sp = add0 + rs;
+      ep = add0 + re;
     }
-    const uint32_t rs = group4_sum(lane_partial_rank2(ks, v, pat, os, j));
-    const uint32_t re = group4_sum(lane_partial_rank2(ke, v, pat, oe, j));
+    rank_pair(lv_last, code & 15u, sp, ep, active, j, rs, re);
     if (active) {
-      const uint32_t add = last ? base : add0;
-      sp_pos = add + rs;
-      ep_pos = add + re;
-      level = 1;
-      if (last) {
-        const uint32_t sp = sp_pos, ep = ep_pos;  // fm_index.cpp:92-93
-        if (sp >= ep) {
-          finish(0, 0, 0);
-        } else if (--rem == 0) {
-          finish(ep - sp, sp, ep);
-        } else {
-          --ptr;
-          begin_step(next_byte, sp, ep);
-        }
+      sp = base + rs;  // fm_index.cpp:92-93
+      ep = base + re;
+      if (sp >= ep) {
+        finish(0, 0, 0);
+      } else if (--rem == 0) {
+        finish(ep - sp, sp, ep);
+      } else {
+        --ptr;
+        begin_step(next_byte);
       }
     }
   }
@@ -138,20 +158,15 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   }
 }
 
-// One level of access(p) fused with rank (both read the same line): returns the nibble at p in
+// One level of access(p) fused with rank (both read the same line): returns the symbol at p in
 // `v` and rank_l(v, p) as the function value. All 32 lanes must call it (shuffles).
-__device__ __forceinline__ uint32_t access_rank_level(const IndexView& iv, uint32_t level, uint32_t p, bool active,
-                                                      int lane, int j, uint32_t& v) {
+__device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane,
+                                                      int j, uint32_t& v) {
   Chunk32 k = {0, 0, 0, 0, 0, 0, 0, 0};
-  const uint32_t off = p & (kSymsPerLine - 1);
-  if (active)
-    k = ldg_nc_v8(iv.levels + (uint64_t)level * iv.level_stride + (uint64_t)(p >> 7) * kLine2Bytes + j * 32);
-  const uint32_t w = off >> 3;  // payload word holding symbol `off`: lane w>>2, component w&3
-  const uint32_t comp = w & 3u;
-  const uint32_t mine = comp == 0 ? k.p0 : comp == 1 ? k.p1 : comp == 2 ? k.p2 : k.p3;
-  const uint32_t wsel = __shfl_sync(0xFFFFFFFFu, mine, (lane & ~3) | (int)(w >> 2));
-  v = (wsel >> (4 * (off & 7u))) & 15u;
-  return group4_sum(lane_partial_rank2(k, v, v * 0x11111111u, off, j));
+  const uint32_t line = p & ~(kSymsPerLine - 1), off = p - line;
+  if (active) k = ldg_nc_v8(lv + line);
+  v = __shfl_sync(0xFFFFFFFFu, chunk_symbol(k, off), (lane & ~3) | (int)(off >> 5));
+  return group4_sum(chunk_partial(chunk_counter(k, v, j), chunk_hits(k, v * 0x11111111u), off, j));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -164,11 +179,13 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
   const int lane = threadIdx.x & 31;
   const int j = lane & 3;
   const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv1 = lv0 + iv.level_stride;
   WarpQueue wq;
 
   bool active = false;
   unsigned long long slot = 0;
-  uint32_t start = 0, p = 0, steps = 0, hi = 0, level = 0;
+  uint32_t start = 0, p = 0, steps = 0;
   uint32_t my_lf = 0;
 
   // Where the reference throws, the whole query fails: attribute the slot to its query.
@@ -205,38 +222,31 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
       start = (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
-      if (start % iv.stride == 0) {
-        emit(start);
-      } else {
-        p = start;
-        level = 0;
-      }
+      p = start;
+      if (start % iv.stride == 0) emit(start);
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
-    uint32_t v;
-    const uint32_t r = access_rank_level(iv, level, p, active, lane, j, v);
+    // ---- one LF step: LF(i) = C[c] + occ(c,i) = base[c] + rank_last(lo, .)  (fm_index.hpp:62-66)
+    uint32_t v, code = 0;
+    uint32_t r = access_rank_level(lv0, p, active, lane, j, v);
+    if (two) {
+      code = v << 4;
+      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v);
+    }
+    code |= v;
     if (active) {
-      if (two && level == 0) {
-        hi = v;
-        p = tb.start1[v] + r;
-        level = 1;
+      const uint32_t row = tb.base_by_code[code] + r;
+      ++steps;
+      ++my_lf;
+      if (row % iv.stride == 0) {
+        emit(row);
+      } else if (row == start || steps >= iv.n) {
+        // LF is a permutation: back at the start without meeting a sampled row means the
+        // reference would walk n steps and throw (fm_index.cpp:130-138).
+        fail_walk((int)CSFM_Q_LF_WALK_EXCEEDED);
       } else {
-        // LF(i) = C[c] + occ(c,i) = base[c] + rank_last(lo, .)   (fm_index.hpp:62-66)
-        const uint32_t code = two ? ((hi << 4) | v) : v;
-        const uint32_t row = tb.base_by_code[code] + r;
-        ++steps;
-        ++my_lf;
-        if (row % iv.stride == 0) {
-          emit(row);
-        } else if (row == start || steps >= iv.n) {
-          // LF is a permutation: back at the start without meeting a sampled row means the
-          // reference would walk n steps and throw (fm_index.cpp:130-138).
-          fail_walk((int)CSFM_Q_LF_WALK_EXCEEDED);
-        } else {
-          p = row;
-          level = 0;
-        }
+        p = row;
       }
     }
   }
@@ -257,6 +267,8 @@ access2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
   const int lane = threadIdx.x & 31;
   const int j = lane & 3;
   const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv1 = lv0 + iv.level_stride;
   const uint64_t group = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 2;
   const uint64_t trips = ((uint64_t)iv.n + ngroups - 1) / ngroups;
@@ -264,11 +276,11 @@ access2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
     const uint64_t i = t * ngroups + group;
     const bool valid = i < iv.n;
     uint32_t v;
-    uint32_t r = access_rank_level(iv, 0, valid ? (uint32_t)i : 0u, valid, lane, j, v);
+    uint32_t r = access_rank_level(lv0, valid ? (uint32_t)i : 0u, valid, lane, j, v);
     uint32_t code = v;
     if (two) {
       const uint32_t hi = v;
-      r = access_rank_level(iv, 1, tb.start1[hi] + r, valid, lane, j, v);
+      r = access_rank_level(lv1, tb.start1[hi] + r, valid, lane, j, v);
       code = (hi << 4) | v;
     }
     if (valid && j == 0) out[i] = tb.byte_of_code[code];
