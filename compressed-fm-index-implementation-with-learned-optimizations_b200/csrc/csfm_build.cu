@@ -310,6 +310,7 @@ int index_finish_handle(csfm_index* idx) {
   const BlobHeader& h = idx->h;
   IndexView& v = idx->view;
   v.levels = idx->d_blob + h.off_levels;
+  v.levels_last = v.levels + (uint64_t)(h.levels - 1) * h.level_stride;
   v.ssa = reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_ssa);
   v.hdr = reinterpret_cast<const BlobHeader*>(idx->d_blob);
   v.level_stride = h.level_stride;

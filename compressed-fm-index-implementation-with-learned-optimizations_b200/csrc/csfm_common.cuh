@@ -84,7 +84,8 @@ static_assert(sizeof(BlobHeader) <= kHeaderBytes, "header grew past its slot");
 
 // What a kernel needs, passed by value.
 struct IndexView {
-  const uint8_t* levels;  // level 0, line 0
+  const uint8_t* levels;       // level 0, line 0
+  const uint8_t* levels_last;  // last level, line 0 (== levels for a one-level index)
   const uint32_t* ssa;
   const BlobHeader* hdr;  // device pointer (tables are staged to shared memory per CTA)
   uint64_t level_stride;
@@ -121,6 +122,15 @@ __device__ __forceinline__ Chunk32 ldg_nc_v8(const void* p) {
   return r;
 }
 
+// A Chunk32 whose registers are "defined" for the compiler without costing an instruction. Lanes
+// that skip the load (inactive sub-warp, or ep in the same line as sp) compute on garbage that is
+// discarded: results only travel inside the 4-lane group and are committed under `if (active)`.
+__device__ __forceinline__ Chunk32 chunk_undefined() {
+  Chunk32 r;
+  asm("" : "=r"(r.c0), "=r"(r.c1), "=r"(r.c2), "=r"(r.c3), "=r"(r.p0), "=r"(r.p1), "=r"(r.p2), "=r"(r.p3));
+  return r;
+}
+
 // mask of the low x bits, x clamped to [0,32]:  high word of (0x00000000FFFFFFFF << min(x,32))
 __device__ __forceinline__ uint32_t low_mask(int x) {
   return __funnelshift_lc(0xFFFFFFFFu, 0u, (uint32_t)max(x, 0));
@@ -150,10 +160,28 @@ __device__ __forceinline__ uint32_t chunk_hits(const Chunk32& k, uint32_t pat) {
   return (nibble_eq_msb(k.p0, pat) >> 3) | (nibble_eq_msb(k.p1, pat) >> 2) | (nibble_eq_msb(k.p2, pat) >> 1) |
          nibble_eq_msb(k.p3, pat);
 }
+// Branch-free pick of one of four registers by a 2-bit index (selp chain: the ternary form
+// compiles to divergent branches).
+__device__ __forceinline__ uint32_t pick4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t idx) {
+  uint32_t r;
+  asm("{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .u32 t0, t1, b0, b1;\n\t"
+      "and.b32 b0, %5, 1;\n\t"
+      "and.b32 b1, %5, 2;\n\t"
+      "setp.ne.u32 p0, b0, 0;\n\t"
+      "setp.ne.u32 p1, b1, 0;\n\t"
+      "selp.u32 t0, %2, %1, p0;\n\t"
+      "selp.u32 t1, %4, %3, p0;\n\t"
+      "selp.u32 %0, t1, t0, p1;\n\t"
+      "}"
+      : "=r"(r)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(idx));
+  return r;
+}
 // cnt[v] if this lane's chunk holds it (lane j holds cnt[4j..4j+3]), else 0
 __device__ __forceinline__ uint32_t chunk_counter(const Chunk32& k, uint32_t v, int j) {
-  const uint32_t comp = v & 3u;
-  const uint32_t cnt = comp == 0 ? k.c0 : comp == 1 ? k.c1 : comp == 2 ? k.c2 : k.c3;
+  const uint32_t cnt = pick4(k.c0, k.c1, k.c2, k.c3, v);
   return ((v >> 2) == (uint32_t)j) ? cnt : 0u;
 }
 // partial rank of lane j for offset off = p & 127, given the lane's counter share and hit word
@@ -162,8 +190,8 @@ __device__ __forceinline__ uint32_t chunk_partial(uint32_t cnt, uint32_t hits, u
 }
 // the symbol at offset off of a line, given this lane's chunk (valid in lane off>>5 only)
 __device__ __forceinline__ uint32_t chunk_symbol(const Chunk32& k, uint32_t off) {
-  const uint32_t s = off & 31u, comp = s & 3u;
-  const uint32_t w = comp == 0 ? k.p0 : comp == 1 ? k.p1 : comp == 2 ? k.p2 : k.p3;
+  const uint32_t s = off & 31u;
+  const uint32_t w = pick4(k.p0, k.p1, k.p2, k.p3, s);
   return (w >> (4u * (s >> 2))) & 15u;
 }
 

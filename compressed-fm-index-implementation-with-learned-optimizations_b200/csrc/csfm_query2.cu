@@ -30,7 +30,7 @@ __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32
   const uint32_t ls = sp_pos & ~(kSymsPerLine - 1), le = ep_pos & ~(kSymsPerLine - 1);  // line*128 == byte offset
   const uint32_t os = sp_pos - ls, oe = ep_pos - le;
   const bool split = active && (le != ls);
-  Chunk32 ks = {0, 0, 0, 0, 0, 0, 0, 0}, ke = ks;
+  Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
   if (active) ks = ldg_nc_v8(lv + ls);
   if (split) ke = ldg_nc_v8(lv + le);
   const uint32_t hs = chunk_hits(ks, pat);
@@ -58,7 +58,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const int j = lane & 3;
   const bool two = iv.L == 2;
   const uint8_t* const lv0 = iv.levels + j * 32;
-  const uint8_t* const lv_last = lv0 + (two ? iv.level_stride : 0);
+  const uint8_t* const lv_last = iv.levels_last + j * 32;
   WarpQueue wq;
 
   bool active = false;
@@ -162,7 +162,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
 // `v` and rank_l(v, p) as the function value. All 32 lanes must call it (shuffles).
 __device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane,
                                                       int j, uint32_t& v) {
-  Chunk32 k = {0, 0, 0, 0, 0, 0, 0, 0};
+  Chunk32 k = chunk_undefined();
   const uint32_t line = p & ~(kSymsPerLine - 1), off = p - line;
   if (active) k = ldg_nc_v8(lv + line);
   v = __shfl_sync(0xFFFFFFFFu, chunk_symbol(k, off), (lane & ~3) | (int)(off >> 5));
@@ -180,7 +180,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
   const int j = lane & 3;
   const bool two = iv.L == 2;
   const uint8_t* const lv0 = iv.levels + j * 32;
-  const uint8_t* const lv1 = lv0 + iv.level_stride;
+  const uint8_t* const lv1 = iv.levels_last + j * 32;
   WarpQueue wq;
 
   bool active = false;
@@ -268,7 +268,7 @@ access2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
   const int j = lane & 3;
   const bool two = iv.L == 2;
   const uint8_t* const lv0 = iv.levels + j * 32;
-  const uint8_t* const lv1 = lv0 + iv.level_stride;
+  const uint8_t* const lv1 = iv.levels_last + j * 32;
   const uint64_t group = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 2;
   const uint64_t trips = ((uint64_t)iv.n + ngroups - 1) / ngroups;
