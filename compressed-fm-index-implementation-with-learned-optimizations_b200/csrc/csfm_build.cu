@@ -307,6 +307,7 @@ int index_finish_handle(csfm_index* idx) {
   cudaDeviceProp prop;
   CSFM_CUDA(cudaGetDeviceProperties(&prop, idx->device));
   idx->num_sms = prop.multiProcessorCount;
+  if (const char* e = std::getenv("CSFM_PATTERN_STAGING")) idx->tma_staging = std::strcmp(e, "tma") == 0;
   const BlobHeader& h = idx->h;
   IndexView& v = idx->view;
   v.levels = idx->d_blob + h.off_levels;

@@ -60,6 +60,7 @@ struct csfm_index {
   void* h_pinned = nullptr;  // small pinned scratch (totals, stats)
 
   uint32_t instr_mask = 0;
+  bool tma_staging = false;  // count kernel variant (csfm_set_option / CSFM_PATTERN_STAGING=tma)
   csfm_call_stats stats{};
   std::mutex mu;
 };

@@ -63,6 +63,55 @@ __device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need
   return item;
 }
 
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX): pattern staging ------------------------
+// cp.async.bulk moves a contiguous, 16-byte aligned span global -> shared through the TMA unit
+// (SASS: UBLKCP) and signals an mbarrier with the byte count; nobody spends registers or issue
+// slots on the copy.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a copy that never lands is a bug — trap (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Orders earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr uint32_t kStageBytes = 2048;  // pattern bytes staged per warp chunk (32 patterns)
+constexpr uint32_t kPrivBytes = 64;     // private slot per sub-warp for the pattern it is working on
+
+// Per-warp double buffer: the packed bytes of a 32-pattern chunk and its kChunk+1 offsets.
+struct alignas(16) WarpStage {
+  uint8_t bytes[2][kStageBytes];
+  uint64_t offs[2][kChunk + 2];
+  const uint8_t* base_ptr[2];  // pattern byte at batch offset o lives at base_ptr[b] + o (shared or global)
+  uint64_t bar_offs[2];
+  uint64_t bar_bytes[2];
+};
+
 struct CountArgs {
   const uint8_t* bytes;
   const uint64_t* offs;
@@ -87,10 +136,10 @@ struct WalkArgs {
 };
 
 // Layout-2 kernels (csfm_query2.cu); launched by the dispatchers in csfm_query.cu.
-void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream);
+void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging);
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
-int max_blocks_per_sm_count2();
+int max_blocks_per_sm_count2(bool tma_staging);
 int max_blocks_per_sm_walk2();
 int max_blocks_per_sm_access2();
 

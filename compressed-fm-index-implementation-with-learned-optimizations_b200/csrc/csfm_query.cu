@@ -314,6 +314,19 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
                  uint64_t* d_counts, uint64_t* d_sp_ep, uint32_t* d_row_sp, uint32_t* d_row_cnt,
                  uint64_t limit, cudaStream_t stream) {
   if (npat == 0) return CSFM_OK;
+  // the kernels index queries with 32 bits: slice larger batches (offsets stay absolute)
+  constexpr uint64_t kMaxPerLaunch = 1ull << 31;
+  if (npat > kMaxPerLaunch) {
+    if (idx->instr_mask & 1u) return fail(CSFM_ERR_INVALID, "step instrumentation needs batches of at most 2^31 patterns");
+    for (uint64_t done = 0; done < npat; done += kMaxPerLaunch) {
+      const uint64_t now = std::min(kMaxPerLaunch, npat - done);
+      int rc = count_device(idx, d_bytes, d_offs + done, now, d_counts ? d_counts + done : nullptr,
+                            d_sp_ep ? d_sp_ep + 2 * done : nullptr, d_row_sp ? d_row_sp + done : nullptr,
+                            d_row_cnt ? d_row_cnt + done : nullptr, limit, stream);
+      if (rc) return rc;
+    }
+    return CSFM_OK;
+  }
   unsigned long long* ctr = next_counter_slot(idx);
   CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
   CountArgs a{};
@@ -328,13 +341,14 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   a.cursor = ctr;
   a.steps_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
-  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2() : persistent_grid(idx, (const void*)count_kernel);
+  const bool tma = idx->tma_staging;
+  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2(tma) : persistent_grid(idx, (const void*)count_kernel);
   const uint64_t want = (npat * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
   if (nib)
-    launch_count2(idx->view, a, grid, stream);
+    launch_count2(idx->view, a, grid, stream, tma);
   else
     count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));

@@ -49,6 +49,8 @@ __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32
 // ------------------------------------------------------------------------------------------
 // count (fm_index.cpp:79-101)
 // ------------------------------------------------------------------------------------------
+// Default variant: pattern offsets and bytes are read straight from global memory (two dependent
+// loads when a sub-warp starts a pattern, then a one-step byte prefetch).
 __global__ void __launch_bounds__(kThreads, 5)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
@@ -131,6 +133,237 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
     // ---- one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
+    uint32_t rs, re;
+    if (two) {
+      rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re);
+      sp = add0 + rs;
+      ep = add0 + re;
+    }
+    rank_pair(lv_last, code & 15u, sp, ep, active, j, rs, re);
+    if (active) {
+      sp = base + rs;  // fm_index.cpp:92-93
+      ep = base + re;
+      if (sp >= ep) {
+        finish(0, 0, 0);
+      } else if (--rem == 0) {
+        finish(ep - sp, sp, ep);
+      } else {
+        --ptr;
+        begin_step(next_byte);
+      }
+    }
+  }
+  if (a.steps_total) {
+    unsigned s = (j == 0) ? my_steps : 0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
+  }
+}
+
+// TMA variant (CSFM_PATTERN_STAGING=tma): every warp stages 32-pattern chunks — their offsets and
+// their packed bytes — into a double buffer in shared memory with cp.async.bulk (UBLKCP) signalled
+// through mbarriers, one chunk ahead of the one being consumed, and sub-warps copy short patterns to
+// a private slot so the buffer can be refilled under them. Measured on B200 (profiles/README.md)
+// it is ~15 % slower than the direct variant on C3: the kernel is bound by issue slots and HBM
+// fetch latency, pattern bytes are 0.1 % of the traffic, and the staging control costs more issue
+// slots than the two dependent loads it removes. Kept selectable and covered by the parity tests.
+__global__ void __launch_bounds__(kThreads, 5)
+count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
+  __shared__ Tables tb;
+  __shared__ WarpStage stages[kThreads / 32];
+  __shared__ __align__(16) uint8_t priv_all[kThreads / 4][kPrivBytes];  // one private pattern slot per sub-warp
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  WarpStage& st = stages[threadIdx.x >> 5];
+  uint8_t* const priv = priv_all[threadIdx.x >> 2];
+  if (lane == 0) {
+    mbar_init(&st.bar_offs[0], 1);
+    mbar_init(&st.bar_offs[1], 1);
+    mbar_init(&st.bar_bytes[0], 1);
+    mbar_init(&st.bar_bytes[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  load_tables(tb, iv.hdr);  // ends with __syncthreads()
+
+  const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv_last = iv.levels_last + j * 32;
+  const uint32_t npat = (uint32_t)a.npat;  // < 2^32 per launch (count_device slices larger batches)
+  // TMA bulk copies need 16-byte aligned sources; otherwise every chunk is read straight from global
+  const bool can_stage = ((reinterpret_cast<uintptr_t>(a.bytes) | reinterpret_cast<uintptr_t>(a.offs)) & 15) == 0;
+
+  // ---- warp-uniform staging state: chunk being consumed + chunk being prefetched -------------
+  uint32_t cur_next = 0, cur_end = 0, cur_base = 0, cur_buf = 1;
+  uint32_t pf_state = 0;  // 0 idle, 1 offsets in flight, 2 chunk ready (bytes in flight / landed / direct)
+  uint32_t pf_base = 0, pf_end = 0;
+  uint32_t par_offs = 0, par_bytes = 0;  // mbarrier phase parity, bit b = buffer b
+  uint32_t direct_mask = 0;              // bit b: chunk in buffer b is read straight from global memory
+  bool exhausted = false;
+
+  // ---- per-sub-warp query state ---------------------------------------------------------------
+  bool active = false;
+  uint32_t q = 0;                // query index
+  const uint8_t* ptr = nullptr;  // address of the character being processed (shared or global)
+  uint32_t rem = 0;              // characters left including the current one
+  uint32_t mybuf = 2;            // staging buffer the pattern bytes live in (2 = global memory)
+  uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
+  uint32_t my_steps = 0;
+
+  auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
+    if (j == 0) {
+      if (a.counts) a.counts[q] = cnt;
+      if (a.sp_ep) {
+        a.sp_ep[2 * (uint64_t)q] = lo;
+        a.sp_ep[2 * (uint64_t)q + 1] = hi;
+      }
+      if (a.row_sp) {
+        a.row_sp[q] = lo;
+        a.row_cnt[q] = cnt < a.limit32 ? cnt : a.limit32;
+      }
+    }
+    active = false;
+  };
+  // Sets up the step that prepends byte b to the interval [sp,ep).
+  auto begin_step = [&](uint32_t b) {
+    ++my_steps;
+    if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
+      finish(0, 0, 0);
+      return;
+    }
+    code = tb.code_of_byte[b];
+    base = tb.base_by_byte[b];
+    add0 = tb.start1[code >> 4];
+    if (rem > 1) next_byte = ptr[-1];  // in flight during the rank levels
+  };
+
+  for (;;) {
+    // ---- A. pattern staging pipeline: TMA bulk copies into the buffer that is not being consumed
+    if (pf_state == 1) {
+      const uint32_t b = cur_buf ^ 1u;
+      // the bytes of the chunk that used to live in buffer b may still be read by a long query
+      if (!__any_sync(0xFFFFFFFFu, active && mybuf == b)) {
+        mbar_wait(&st.bar_offs[b], (par_offs >> b) & 1u);
+        par_offs ^= 1u << b;
+        int direct = 1;
+        if (lane == 0) {
+          const uint64_t o_first = st.offs[b][0], o_last = st.offs[b][pf_end - pf_base];
+          const uint8_t* src = a.bytes + o_first;
+          const uint8_t* src_al = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15);
+          const uint64_t span = (uint64_t)(src - src_al) + (o_last - o_first);
+          const bool tail_overrun = (pf_end == npat) && ((span & 15) != 0);  // rounding up would read past the batch
+          if (o_last != o_first && span <= kStageBytes && !tail_overrun) {
+            const uint32_t size = (uint32_t)((span + 15) & ~15ull);
+            fence_proxy_async_smem();
+            mbar_expect_tx(&st.bar_bytes[b], size);
+            tma_bulk_g2s(st.bytes[b], src_al, size, &st.bar_bytes[b]);
+            st.base_ptr[b] = st.bytes[b] - (src_al - a.bytes);
+            direct = 0;
+          } else {
+            st.base_ptr[b] = a.bytes;
+          }
+        }
+        direct = __shfl_sync(0xFFFFFFFFu, direct, 0);
+        direct_mask = (direct_mask & ~(1u << b)) | ((uint32_t)direct << b);
+        __syncwarp();
+        pf_state = 2;
+      }
+    } else if (pf_state == 0 && !exhausted) {
+      unsigned long long cbase = 0;
+      if (lane == 0) cbase = atomicAdd(a.cursor, (unsigned long long)kChunk);
+      cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+      if (cbase >= a.npat) {
+        exhausted = true;
+      } else {
+        pf_base = (uint32_t)cbase;
+        pf_end = (pf_base + kChunk < npat) ? pf_base + kChunk : npat;
+        const uint32_t b = cur_buf ^ 1u;
+        const uint32_t ents = (pf_end - pf_base + 2u) & ~1u;  // count+1 offsets, rounded up to 16 bytes
+        if (can_stage && (uint64_t)pf_base + ents <= (uint64_t)npat + 1) {
+          if (lane == 0) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(&st.bar_offs[b], ents * 8u);
+            tma_bulk_g2s(st.offs[b], a.offs + pf_base, ents * 8u, &st.bar_offs[b]);
+          }
+          pf_state = 1;
+        } else {
+          if (lane == 0) st.base_ptr[b] = a.bytes;
+          direct_mask |= 1u << b;
+          __syncwarp();
+          pf_state = 2;
+        }
+      }
+    }
+
+    // ---- B. refill (every sub-warp is at a step boundary here) ------------------------------
+    const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, !active) & 0x11111111u;
+    if (need_mask) {
+      if (cur_next >= cur_end && pf_state == 2) {  // switch to the prefetched chunk
+        const uint32_t b = cur_buf ^ 1u;
+        if (!((direct_mask >> b) & 1u)) {
+          mbar_wait(&st.bar_bytes[b], (par_bytes >> b) & 1u);
+          par_bytes ^= 1u << b;
+        }
+        cur_buf = b;
+        cur_base = cur_next = pf_base;
+        cur_end = pf_end;
+        pf_state = 0;
+      }
+      const uint32_t avail = cur_end - cur_next;
+      const uint32_t my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
+      const uint32_t cnt = __popc(need_mask);
+      if (!active && my_rank < avail) {
+        q = cur_next + my_rank;
+        const bool dir = (direct_mask >> cur_buf) & 1u;
+        uint64_t o0, o1;
+        if (dir) {
+          o0 = a.offs[q];
+          o1 = a.offs[q + 1];
+        } else {
+          o0 = st.offs[cur_buf][q - cur_base];
+          o1 = st.offs[cur_buf][q - cur_base + 1];
+        }
+        const uint8_t* pb = st.base_ptr[cur_buf];
+        const uint64_t m = o1 - o0;
+        mybuf = dir ? 2u : cur_buf;
+        if (!dir && m <= kPrivBytes) {
+          // Short pattern of a staged chunk: move it to the sub-warp's private slot so that the
+          // chunk buffer can be refilled by TMA while this query is still running.
+          for (uint32_t k = j; k < (uint32_t)m; k += 4) priv[k] = pb[o0 + k];
+          pb = priv - o0;
+          mybuf = 2u;
+        }
+        active = true;
+        if (m == 0) {
+          // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
+          if (j == 0) {
+            if (a.counts) a.counts[q] = iv.n;
+            if (a.sp_ep) { a.sp_ep[2 * (uint64_t)q] = 0; a.sp_ep[2 * (uint64_t)q + 1] = 0; }
+            if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
+          }
+          active = false;
+        } else {
+          // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
+          const uint32_t b = pb[o1 - 1];
+          sp = tb.C[b];
+          ep = tb.C[b + 1];
+          ++my_steps;
+          if (sp >= ep) {
+            finish(0, 0, 0);
+          } else if (m == 1) {
+            finish(ep - sp, sp, ep);
+          } else {
+            rem = (uint32_t)(m - 1);
+            ptr = pb + (o1 - 2);
+            begin_step(*ptr);
+          }
+        }
+      }
+      cur_next += (cnt < avail) ? cnt : avail;
+      __syncwarp();  // private-slot writes of a sub-warp are read by all of its four lanes
+    }
+    if (exhausted && pf_state == 0 && cur_next >= cur_end && !__any_sync(0xFFFFFFFFu, active)) break;
+
+    // ---- C. one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
     uint32_t rs, re;
     if (two) {
       rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re);
@@ -295,8 +528,11 @@ int blocks_per_sm(const void* kernel) {
 
 }  // namespace
 
-void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream) {
-  count2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging) {
+  if (tma_staging)
+    count2_tma_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+  else
+    count2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
 }
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
   walk2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
@@ -304,7 +540,9 @@ void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
   access2_kernel<<<grid, kThreads, 0, stream>>>(iv, out);
 }
-int max_blocks_per_sm_count2() { return blocks_per_sm((const void*)count2_kernel); }
+int max_blocks_per_sm_count2(bool tma_staging) {
+  return blocks_per_sm(tma_staging ? (const void*)count2_tma_kernel : (const void*)count2_kernel);
+}
 int max_blocks_per_sm_walk2() { return blocks_per_sm((const void*)walk2_kernel); }
 int max_blocks_per_sm_access2() { return blocks_per_sm((const void*)access2_kernel); }
 

@@ -266,3 +266,53 @@ def test_device_pointer_api(fm):
     assert (toffs.cpu().numpy().astype(np.uint64) == ooffs).all()
     assert (tpos.cpu().numpy().astype(np.uint64)[:total] == opos).all()
     assert (tst.cpu().numpy() == ostatus).all()
+
+
+def test_unaligned_and_odd_sized_device_batches(fm):
+    """Pattern staging uses 16-byte aligned TMA bulk copies: unaligned batches, batches whose size
+    is not a multiple of the 32-query chunk, empty-only chunks and oversized chunks must all take
+    the direct path and give the same answers."""
+    import torch
+    rng = np.random.default_rng(21)
+    text, alpha = _rand_text(rng, 120_000, 7, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=8))
+    orc = oracle.OracleIndex(text, stride=8)
+    dev = torch.device("cuda:0")
+    for npat, maxlen, shift_b, shift_o in [(1, 9, 0, 0), (31, 9, 0, 0), (33, 9, 3, 0), (64, 9, 0, 1), (1000, 9, 5, 1),
+                                           (4097, 40, 0, 0), (257, 300, 0, 0), (96, 0, 0, 0)]:
+        pats = [text[s:s + m].tobytes() for s, m in zip(rng.integers(0, 100_000, npat), rng.integers(0, maxlen + 1, npat))]
+        d, o = fm.pack_patterns(pats)
+        oc, ose = orc.count_batch(d, o)
+        # place the arrays at deliberately misaligned device addresses
+        tb = torch.zeros(d.size + 64, dtype=torch.uint8, device=dev)
+        tb[shift_b:shift_b + d.size] = torch.from_numpy(d).to(dev)
+        to = torch.zeros(o.size + 8, dtype=torch.int64, device=dev)
+        to[shift_o:shift_o + o.size] = torch.from_numpy(o.astype(np.int64)).to(dev)
+        tc = torch.zeros(npat, dtype=torch.int64, device=dev)
+        tse = torch.zeros(2 * npat, dtype=torch.int64, device=dev)
+        idx.count_batch_device(tb.data_ptr() + shift_b, to.data_ptr() + 8 * shift_o, npat, tc.data_ptr(), tse.data_ptr(), 0)
+        torch.cuda.synchronize()
+        assert (tc.cpu().numpy().astype(np.uint64) == oc).all(), (npat, maxlen, shift_b, shift_o)
+        assert (tse.cpu().numpy().astype(np.uint64).reshape(-1, 2) == ose).all()
+
+
+def test_tma_staged_count_variant(fm, monkeypatch):
+    """The TMA-staged count kernel (CSFM_PATTERN_STAGING=tma: cp.async.bulk + mbarrier double
+    buffer per warp) must agree with the oracle exactly like the default direct-load kernel."""
+    monkeypatch.setenv("CSFM_PATTERN_STAGING", "tma")
+    rng = np.random.default_rng(77)
+    for sigma, n, flags in [(4, 150_000, 0), (200, 200_000, 0)]:
+        text, alpha = _rand_text(rng, n, sigma, True)
+        idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16), flags=flags)
+        orc = oracle.OracleIndex(text, stride=16)
+        pats = _mixed_patterns(rng, text, alpha, 20_000, 40)
+        pats += [text[s:s + m].tobytes() for s, m in zip(rng.integers(0, n - 3000, 40), rng.integers(65, 2500, 40))]
+        d, o = fm.pack_patterns(pats)
+        idx.set_instrumentation(1)
+        counts, sp_ep = idx.count_batch(d, o, want_intervals=True)
+        oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
+        assert (counts == oc).all() and (sp_ep == ose).all()
+        assert idx.last_call_stats().search_steps == int(osteps.sum())
+        offs, pos, status = idx.locate_batch(d, o, limit=11)
+        ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=11)
+        assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
