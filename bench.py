@@ -376,11 +376,12 @@ def run_engine(args, rank, world, local_rank):
 
     # exact executed-step counts per batch (S of the roofline model) + correctness properties
     idx.set_instrumentation(1)
-    steps_per_batch = []
+    steps_per_batch, lookups_per_batch = [], []
     for b in range(NB):
         step_device(b)
         stream.synchronize()
         steps_per_batch.append(int(idx.last_call_stats().search_steps))
+        lookups_per_batch.append(int(idx.last_call_stats().table_lookups))
         if b == 0:
             c0 = d_counts.cpu().numpy().copy()
             assert (c0 >= 1).all(), "text-sampled patterns must occur at least once"
@@ -446,7 +447,8 @@ def run_engine(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (count_kernel) ------------------------------------------------
     peak, peak_src = measured_peak()
     line_bytes = int(info.line_bytes)
-    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes for i in range(args.steps)]
+    # executed traffic model: every rank step reads 2 x L lines, every k-mer table lookup one line
+    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + lookups_per_batch[i % NB] * 128 for i in range(args.steps)]
     achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
@@ -459,6 +461,8 @@ def run_engine(args, rank, world, local_rank):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
                 "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
+                "table_lookups_per_launch": float(np.mean([lookups_per_batch[i % NB] for i in range(args.steps)])),
+                "kmer_k": int(info.kmer_k),
                 "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
                 "note": "duration per launch = CUDA events on the launching stream around each step "
                         "(32-byte cursor memset + count_kernel)"}

@@ -192,6 +192,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->has_sa = idx->d_sa != nullptr;
   out->layout = idx->h.layout;
   out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;
+  out->kmer_k = idx->view.kmer_k;
   return CSFM_OK;
 }
 
@@ -266,6 +267,13 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
       h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * line_bytes ||
       h.nsamp != (h.n + h.stride - 1) / h.stride)
     return fail(CSFM_ERR_FORMAT, "inconsistent blob header");
+  if (h.kmer_k) {
+    uint64_t entries = 1;
+    for (uint32_t i = 0; i < h.kmer_k && entries <= (1ull << 40); ++i) entries *= h.kmer_radix;
+    if (!nib || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
+        h.off_kmer + entries * 8 > h.total_bytes)
+      return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
+  }
   auto* idx = new (std::nothrow) csfm_index();
   if (!idx) return fail(CSFM_ERR_NOMEM, "host allocation failed");
   idx->device = device;
@@ -322,7 +330,12 @@ static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
   // caller has synchronised `stream`
   const unsigned long long* hp = static_cast<const unsigned long long*>(idx->h_pinned);
   if (idx->instr_mask & 1u) {
-    if (locate) idx->stats.lf_steps = hp[9]; else idx->stats.search_steps = hp[8];
+    if (locate) {
+      idx->stats.lf_steps = hp[9];
+    } else {
+      idx->stats.search_steps = hp[8];
+      idx->stats.table_lookups = (uint32_t)hp[10];
+    }
   }
   if (idx->instr_mask & 2u) {
     float ms = 0.f;
@@ -456,6 +469,7 @@ int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out) {
   const unsigned long long* hp = static_cast<const unsigned long long*>(idx->h_pinned);
   if (idx->instr_mask & 1u) {
     if (!out->search_steps) out->search_steps = hp[8];
+    if (!out->table_lookups) out->table_lookups = (uint32_t)hp[10];
     if (!out->lf_steps) out->lf_steps = hp[9];
   }
   if ((idx->instr_mask & 2u) && out->kernel_ms == 0.f) {

@@ -320,6 +320,13 @@ int index_finish_handle(csfm_index* idx) {
   v.stride = h.stride;
   v.nsamp = (uint32_t)h.nsamp;
   v.layout = h.layout;
+  v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
+  v.kmer_k = h.kmer_k;
+  v.kmer_radix = h.kmer_radix;
+  if (std::getenv("CSFM_NO_KMER_TABLE")) {  // experiment knob: ignore a table that is present
+    v.kmer = nullptr;
+    v.kmer_k = 0;
+  }
   for (int l = 0; l < (int)kMaxLevels; ++l) v.zeros[l] = h.zeros[l];
   if (!idx->stream) CSFM_CUDA(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
   if (!idx->ev0) CSFM_CUDA(cudaEventCreate(&idx->ev0));
@@ -365,6 +372,24 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   h.level_stride = align_up(h.nblk * (nib ? kLine2Bytes : kLineBytes), 256);
   h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
   h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
+  // k-mer jump table: the first k steps of a query become one lookup. Budget: a quarter of the
+  // level bytes, between 1 MiB and 128 MiB (k = 3 for a byte alphabet at n = 2^30, 9 for DNA+$ at 2^26).
+  if (nib && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
+    const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : h.sigma;
+    const uint64_t budget = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
+    uint32_t k = 0;
+    uint64_t entries = 1;
+    while (radix >= 2 && entries * radix * 8 <= budget && k < 16) {
+      entries *= radix;
+      ++k;
+    }
+    if (k >= 2) {
+      h.kmer_k = k;
+      h.kmer_radix = (uint32_t)radix;
+      h.off_kmer = h.total_bytes;
+      h.total_bytes = align_up(h.off_kmer + entries * 8, 256);
+    }
+  }
 
   idx->blob_bytes = h.total_bytes;
   idx->owns_blob = true;
@@ -460,6 +485,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   cleanup();
 #undef BUILD_CUDA
   int rc = index_finish_handle(idx);
+  if (rc == CSFM_OK && h.kmer_k) rc = build_kmer_table(idx, st);  // runs backward search over the finished levels
   if (rc != CSFM_OK) {
     csfm_destroy(idx);
     return rc;

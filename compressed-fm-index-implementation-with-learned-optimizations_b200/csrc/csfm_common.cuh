@@ -68,7 +68,12 @@ struct BlobHeader {
   uint32_t zeros[kMaxLevels];  // layout 1: number of 0 bits per level
   uint32_t layout;             // kLayoutBinary64 | kLayoutNibble128
   uint32_t code_bits;          // B
-  uint32_t reserved0[14];
+  // k-mer jump table (layout 2): entry e = (sp,ep) of the k-symbol string whose LAST symbol has
+  // code e % radix, the one before it (e / radix) % radix, ...; (0,0) when it does not occur.
+  uint32_t kmer_k;             // 0 = no table
+  uint32_t kmer_radix;         // number of compact codes (sigma, or 256 with NO_COMPACT)
+  uint64_t off_kmer;           // byte offset of the table (uint2 entries)
+  uint32_t reserved0[10];
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
@@ -88,6 +93,9 @@ struct IndexView {
   const uint8_t* levels_last;  // last level, line 0 (== levels for a one-level index)
   const uint32_t* ssa;
   const BlobHeader* hdr;  // device pointer (tables are staged to shared memory per CTA)
+  const uint2* kmer;      // k-mer jump table or nullptr
+  uint32_t kmer_k;
+  uint32_t kmer_radix;
   uint64_t level_stride;
   uint32_t n;
   uint32_t L;

@@ -73,6 +73,7 @@ constexpr uint32_t kCounterSlots = 256;  // each slot = 4 x u64
 int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ssa, uint64_t nsamp,
                           uint32_t stride, int device, uint32_t flags, csfm_index** out);
 int index_finish_handle(csfm_index* idx);  // fills view/stream/workspace after d_blob + h are set
+int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: fills the table section
 // csfm_sa.cu
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,

@@ -16,6 +16,8 @@
 // Replaces cs::FMIndex::count / locate (/root/reference/src/api/fm_index.cpp:79-157),
 // cs::WaveletTree::rank / access (src/core/wavelet.cpp:59-128) and cs::BitVector::rank1
 // (src/core/bitvector.cpp:165-230).
+#include <algorithm>
+
 #include "csfm_host.hpp"
 #include "csfm_kernels.cuh"
 
@@ -61,6 +63,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const bool two = iv.L == 2;
   const uint8_t* const lv0 = iv.levels + j * 32;
   const uint8_t* const lv_last = iv.levels_last + j * 32;
+  const uint32_t kk = iv.kmer_k;  // 0 = no jump table
   WarpQueue wq;
 
   bool active = false;
@@ -68,7 +71,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const uint8_t* ptr = nullptr;  // address of the character being processed
   uint32_t rem = 0;              // characters left including the current one
   uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
-  uint32_t my_steps = 0;
+  uint32_t my_steps = 0, my_lookups = 0;
 
   auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
     if (j == 0) {
@@ -113,6 +116,31 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
         }
         active = false;
+      } else if (kk != 0 && m >= kk) {
+        // k-mer jump table: the interval of the last k characters in one lookup (the table was
+        // filled by this same backward search, kmer_build_kernel)
+        uint32_t e = 0, mul = 1;
+        bool present = true;
+        for (uint32_t i = 0; i < kk; ++i) {
+          const uint32_t b = a.bytes[o1 - 1 - i];
+          present = present && (tb.C[b + 1] != tb.C[b]);
+          e += tb.code_of_byte[b] * mul;
+          mul *= iv.kmer_radix;
+        }
+        ++my_lookups;
+        uint2 se = make_uint2(0, 0);
+        if (present) se = iv.kmer[e];
+        sp = se.x;
+        ep = se.y;
+        if (sp >= ep) {
+          finish(0, 0, 0);
+        } else if (m == kk) {
+          finish(ep - sp, sp, ep);
+        } else {
+          rem = (uint32_t)(m - kk);
+          ptr = a.bytes + (o1 - 1 - kk);
+          begin_step(*ptr);
+        }
       } else {
         // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
         const uint32_t b = a.bytes[o1 - 1];
@@ -154,9 +182,56 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
   }
   if (a.steps_total) {
-    unsigned s = (j == 0) ? my_steps : 0;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+    }
     if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
+    if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
+  }
+}
+
+// Fills the k-mer jump table by running the same backward search over every k-symbol string:
+// entry e decodes to codes d_0 (LAST character, e % radix), d_1, ... and stores its interval.
+__global__ void __launch_bounds__(kThreads)
+kmer_build_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ table, unsigned long long entries, uint32_t k,
+                  uint32_t radix) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv_last = iv.levels_last + j * 32;
+  const unsigned long long group = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const unsigned long long ngroups = ((unsigned long long)gridDim.x * blockDim.x) >> 2;
+  const unsigned long long trips = (entries + ngroups - 1) / ngroups;
+  for (unsigned long long t = 0; t < trips; ++t) {
+    const unsigned long long e = t * ngroups + group;
+    const bool valid = e < entries;
+    unsigned long long rest = valid ? e : 0;
+    uint32_t byte = tb.byte_of_code[rest % radix];
+    rest /= radix;
+    uint32_t sp = tb.C[byte], ep = tb.C[byte + 1];  // first step: [C[c], C[c+1])
+    bool alive = valid && sp < ep;
+    for (uint32_t i = 1; i < k; ++i) {
+      const uint32_t code = (uint32_t)(rest % radix);
+      rest /= radix;
+      byte = tb.byte_of_code[code];
+      const bool act = alive && (tb.C[byte + 1] != tb.C[byte]);
+      uint32_t rs, re;
+      if (two) {
+        rank_pair(lv0, code >> 4, sp, ep, act, j, rs, re);
+        sp = tb.start1[code >> 4] + rs;
+        ep = tb.start1[code >> 4] + re;
+      }
+      rank_pair(lv_last, code & 15u, sp, ep, act, j, rs, re);
+      sp = tb.base_by_code[code] + rs;
+      ep = tb.base_by_code[code] + re;
+      alive = act && sp < ep;
+    }
+    if (valid && j == 0) table[e] = alive ? make_uint2(sp, ep) : make_uint2(0u, 0u);
   }
 }
 
@@ -534,6 +609,23 @@ void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream
   else
     count2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
 }
+int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
+  const BlobHeader& h = idx->h;
+  if (!h.kmer_k) return CSFM_OK;
+  unsigned long long entries = 1;
+  for (uint32_t i = 0; i < h.kmer_k; ++i) entries *= h.kmer_radix;
+  uint2* table = reinterpret_cast<uint2*>(idx->d_blob + h.off_kmer);
+  const unsigned long long want = (entries * 4 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm((const void*)kmer_build_kernel));
+  IndexView v = idx->view;  // the table is being written: the builder itself must not consult it
+  v.kmer = nullptr;
+  v.kmer_k = 0;
+  kmer_build_kernel<<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
+  CSFM_CUDA(cudaGetLastError());
+  CSFM_CUDA(cudaStreamSynchronize(stream));
+  return CSFM_OK;
+}
+
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
   walk2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
 }

@@ -72,6 +72,8 @@ typedef struct {
 #define CSFM_BUILD_LAYOUT_BINARY64 4u /* layout 1: binary wavelet matrix in 64-byte lines (one bit
                                          per line fetch) instead of the default layout 2: 16-ary
                                          levels in 128-byte lines (four bits per line fetch) */
+#define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
+                                       default: the first k steps of a query become one lookup) */
 
 typedef struct {
   uint64_t n;          /* text length (cs::IndexMeta::n, fm_index.hpp:15) */
@@ -86,17 +88,19 @@ typedef struct {
   uint32_t has_sa;     /* full SA still resident (CSFM_BUILD_KEEP_SA) */
   uint32_t layout;     /* 1 = binary / 64-byte lines, 2 = 16-ary / 128-byte lines */
   uint32_t line_bytes; /* bytes fetched per rank per level: 64 or 128 */
-  uint32_t reserved;
+  uint32_t kmer_k;     /* length of the k-mer jump table's keys, 0 = no table */
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */
 typedef struct {
   uint64_t kernel_launches; /* CUDA kernels this library launched in the call */
   uint64_t h2d_bytes, d2h_bytes;
-  uint64_t search_steps;    /* executed backward-search steps (S of SURVEY §8d); 0 unless asked */
+  uint64_t search_steps;    /* backward-search steps executed through rank (incl. the free first
+                               step of queries that did not use the table); 0 unless asked */
   uint64_t lf_steps;        /* LF steps walked by locate; 0 unless asked */
   float kernel_ms;          /* device time of the dominant kernel (CUDA events), 0 unless asked */
-  uint32_t reserved;
+  uint32_t table_lookups;   /* queries that started from the k-mer table (their first k steps are
+                               not in search_steps); 0 unless asked */
 } csfm_call_stats;
 
 CSFM_API const char* csfm_last_error(void);

@@ -147,13 +147,26 @@ def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
     assert (idx.ssa() == orc.ssa).all()
     pats = _mixed_patterns(rng, text, alpha, 3000, 24)
     d, o = fm.pack_patterns(pats)
+    oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
     idx.set_instrumentation(1)
     counts, sp_ep = idx.count_batch(d, o, want_intervals=True)
-    steps_gpu = idx.last_call_stats().search_steps
-    oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
+    st = idx.last_call_stats()
     assert (counts == oc).all()
     assert (sp_ep == ose).all()
-    assert steps_gpu == int(osteps.sum())  # the S of the roofline model is counted exactly
+    kk = idx.info().kmer_k
+    if kk == 0:
+        assert st.search_steps == int(osteps.sum())  # the S of the roofline model is counted exactly
+    else:
+        # queries of length >= k start from the k-mer jump table: same answers, fewer rank steps
+        lens = np.diff(o).astype(np.int64)
+        assert st.table_lookups == int((lens >= kk).sum())
+        assert st.search_steps <= int(osteps.sum())
+        plain = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=flags | fm.BUILD_NO_KMER_TABLE)
+        assert plain.info().kmer_k == 0
+        plain.set_instrumentation(1)
+        c2, se2 = plain.count_batch(d, o, want_intervals=True)
+        assert (c2 == oc).all() and (se2 == ose).all()
+        assert plain.last_call_stats().search_steps == int(osteps.sum())
     for limit in (100000, 7):
         offs, pos, status = idx.locate_batch(d, o, limit=limit)
         lf_gpu = idx.last_call_stats().lf_steps
