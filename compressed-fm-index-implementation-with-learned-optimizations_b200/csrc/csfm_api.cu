@@ -163,6 +163,8 @@ void csfm_destroy(csfm_index* idx) {
   if (!idx) return;
   DeviceGuard g(idx->device);
   if (idx->stream) cudaStreamSynchronize(idx->stream);
+  for (auto& s : idx->aux_stream)
+    if (s) cudaStreamSynchronize(s);
   if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
   if (idx->d_sa) cudaFree(idx->d_sa);
   idx->ws_in.release();
@@ -175,6 +177,8 @@ void csfm_destroy(csfm_index* idx) {
   if (idx->ev0) cudaEventDestroy(idx->ev0);
   if (idx->ev1) cudaEventDestroy(idx->ev1);
   if (idx->stream) cudaStreamDestroy(idx->stream);
+  for (auto& s : idx->aux_stream)
+    if (s) cudaStreamDestroy(s);
   delete idx;
 }
 
@@ -375,15 +379,42 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + offs_bytes;
   uint64_t* d_counts = idx->ws_out.as<uint64_t>();
   uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
-  CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, st));
-  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
-  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, st);
-  if (rc) return rc;
-  CSFM_CUDA(cudaMemcpyAsync(counts, d_counts, npat * 8, cudaMemcpyDeviceToHost, st));
-  if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, st));
-  CSFM_CUDA(cudaStreamSynchronize(st));
   idx->stats.h2d_bytes = offs_bytes + nbytes;
   idx->stats.d2h_bytes = out_bytes;
+
+  // Large batches are pipelined: slices on alternating streams, so that the host->device copy of
+  // slice i+1 and the device->host copy of slice i-1 overlap the kernel of slice i, and the
+  // persistent CTAs of consecutive slices hand the SMs over without a gap. Offsets stay absolute,
+  // so a slice's bytes land at the same positions of the device buffer as in one big copy.
+  constexpr uint64_t kMinSlice = 1ull << 16;
+  const uint64_t nslices = (idx->instr_mask == 0 && npat >= 4 * kMinSlice) ? 4 : 1;
+  if (nslices == 1) {
+    CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, st));
+    if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, st));
+    rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    CSFM_CUDA(cudaMemcpyAsync(counts, d_counts, npat * 8, cudaMemcpyDeviceToHost, st));
+    if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, st));
+    CSFM_CUDA(cudaStreamSynchronize(st));
+    return end_call(idx, st, false);
+  }
+  for (int s = 0; s < 2; ++s)
+    if (!idx->aux_stream[s]) CSFM_CUDA(cudaStreamCreateWithFlags(&idx->aux_stream[s], cudaStreamNonBlocking));
+  for (uint64_t s = 0; s < nslices; ++s) {
+    const uint64_t lo = npat * s / nslices, hi = npat * (s + 1) / nslices;
+    cudaStream_t ss = idx->aux_stream[s & 1];
+    // offsets lo..hi inclusive (the shared boundary entry is copied twice with the same value)
+    CSFM_CUDA(cudaMemcpyAsync(d_offs + lo, offs + lo, (hi - lo + 1) * 8, cudaMemcpyHostToDevice, ss));
+    const uint64_t b0 = offs[lo], b1 = offs[hi];
+    if (b1 > b0) CSFM_CUDA(cudaMemcpyAsync(d_bytes + b0, bytes + b0, b1 - b0, cudaMemcpyHostToDevice, ss));
+    rc = count_device(idx, d_bytes, d_offs + lo, hi - lo, d_counts + lo, d_sp_ep ? d_sp_ep + 2 * lo : nullptr, nullptr,
+                      nullptr, 0, ss);
+    if (rc) return rc;
+    CSFM_CUDA(cudaMemcpyAsync(counts + lo, d_counts + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, ss));
+    if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep + 2 * lo, d_sp_ep + 2 * lo, (hi - lo) * 16, cudaMemcpyDeviceToHost, ss));
+  }
+  CSFM_CUDA(cudaStreamSynchronize(idx->aux_stream[0]));
+  CSFM_CUDA(cudaStreamSynchronize(idx->aux_stream[1]));
   return end_call(idx, st, false);
 }
 

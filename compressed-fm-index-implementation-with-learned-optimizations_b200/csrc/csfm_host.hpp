@@ -53,6 +53,7 @@ struct csfm_index {
   uint32_t* d_sa = nullptr;  // CSFM_BUILD_KEEP_SA
 
   cudaStream_t stream = nullptr;  // used by the host-pointer API
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};  // slice pipeline of large host-pointer batches
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
   unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators
