@@ -53,6 +53,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE line may reach stdout (the JSON line). Libraries write banners to fd 1 (NCCL prints
+# its version there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -215,16 +227,20 @@ def run_reference(args, rank, world):
     nthreads = os.cpu_count() or 1
     bytes_d, offs_d = make_batch(wl, text, 0, min(wl["batch"], 200_000))
     data, offs = bytes_d.cpu().numpy(), offs_d.cpu().numpy().astype(np.uint64)
-    # calibrate the per-step sample so that (steps + warmup) samples fit in ~90 s
+    # Size the per-step sample so that warmup + steps end in ~2 minutes whatever K is. Each query is
+    # one std::thread's work, so a step with fewer queries than cores keeps only that many cores busy
+    # (reported in `cores`); with few steps every core works.
     _, q0, dt0 = reference_timed_sample(ref, data, offs, 0.0, nthreads)
-    per_step = max(nthreads, int((q0 / dt0) * 90.0 / (args.steps + args.warmup)))
-    per_step = min(per_step, (offs.size - 1) // 2)
+    rate = q0 / dt0  # queries/s with all cores busy
+    per_step = int(rate * 120.0 / (args.steps + args.warmup))
+    per_step = max(1, min(per_step, (offs.size - 1) // 2))
+    threads_used = min(nthreads, per_step)
     total_q, total_t, cursor = 0, 0.0, 0
     for i in range(args.warmup + args.steps):
         lo = cursor % (offs.size - 1 - per_step)
         o = offs[lo: lo + per_step + 1]
         t = time.perf_counter()
-        ref.count_batch(data, o, nthreads=nthreads)
+        ref.count_batch(data, o, nthreads=threads_used)
         dt = time.perf_counter() - t
         cursor += per_step
         if i >= args.warmup:
@@ -238,12 +254,13 @@ def run_reference(args, rank, world):
         "config": {"workload": wl["desc"], "n": n, "queries_per_step": per_step,
                    "note": "reference cs::FMIndex::count verbatim on host cores; its index is injected from the GPU-built "
                            "BWT (untimed setup) because build_sa_naive is O(n^2 log n)"},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": nthreads, "kind": "reference",
-                         "sample": f"{per_step} queries per step x {args.steps} steps of the first batch, std::thread x {nthreads}"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads_used, "kind": "reference",
+                         "sample": f"{per_step} queries per step x {args.steps} steps of the first batch on {threads_used} of "
+                                   f"{nthreads} host threads (all-core calibration: {rate:.2f} q/s)"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 
@@ -518,7 +535,7 @@ def run_engine(args, rank, world, local_rank):
         "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal},
         "locate": locate,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
