@@ -77,6 +77,8 @@ SIGNATURES = {
     "csfm_from_host_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "csfm_count_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp]),
     "csfm_count_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
+    "csfm_count_batch_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "csfm_count_batch_wait": (C.c_int, [_vp, C.c_uint64]),
     "csfm_locate_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_locate_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp,
                                            C.POINTER(C.c_uint64), _vp]),
@@ -304,6 +306,16 @@ class FMIndex:
                                               _vp(d_status) if d_status else None, C.byref(total),
                                               _vp(stream) if stream else None))
         return int(total.value)
+
+    def count_batch_submit(self, bytes_ptr: int, offs_ptr: int, npat: int, counts_ptr: int, sp_ep_ptr: int = 0) -> int:
+        """Asynchronous count over raw (pinned) host pointers; returns a ticket for count_batch_wait."""
+        t = C.c_uint64()
+        _check(lib().csfm_count_batch_submit(self._h, _vp(bytes_ptr), _vp(offs_ptr), npat, _vp(counts_ptr),
+                                             _vp(sp_ep_ptr) if sp_ep_ptr else None, C.byref(t)))
+        return int(t.value)
+
+    def count_batch_wait(self, ticket: int):
+        _check(lib().csfm_count_batch_wait(self._h, ticket))
 
     # ---- the reference's single-query API -----------------------------------------------------
     def count(self, pattern) -> int:

@@ -165,6 +165,14 @@ void csfm_destroy(csfm_index* idx) {
   if (idx->stream) cudaStreamSynchronize(idx->stream);
   for (auto& s : idx->aux_stream)
     if (s) cudaStreamSynchronize(s);
+  for (auto& sl : idx->async_slot) {
+    if (sl.stream) {
+      cudaStreamSynchronize(sl.stream);
+      cudaStreamDestroy(sl.stream);
+    }
+    sl.in.release();
+    sl.out.release();
+  }
   if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
   if (idx->d_sa) cudaFree(idx->d_sa);
   idx->ws_in.release();
@@ -416,6 +424,60 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   CSFM_CUDA(cudaStreamSynchronize(idx->aux_stream[0]));
   CSFM_CUDA(cudaStreamSynchronize(idx->aux_stream[1]));
   return end_call(idx, st, false);
+}
+
+int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
+                            uint64_t* sp_ep, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!offs || !counts))) return fail(CSFM_ERR_INVALID, "null argument");
+  const uint64_t nbytes = npat ? offs[npat] : 0;
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const uint64_t t = idx->next_ticket++;
+  csfm_index::AsyncSlot& sl = idx->async_slot[t % CSFM_ASYNC_SLOTS];
+  if (!sl.stream) CSFM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  if (sl.ticket) CSFM_CUDA(cudaStreamSynchronize(sl.stream));  // slot still busy with an older batch
+  sl.ticket = t;
+  *ticket = t;
+  if (npat == 0) return CSFM_OK;
+  const size_t offs_bytes = (npat + 1) * 8;
+  int rc = sl.in.ensure(offs_bytes + nbytes + 16);
+  if (rc) return rc;
+  rc = sl.out.ensure(npat * 8 * (sp_ep ? 3 : 1));
+  if (rc) return rc;
+  uint64_t* d_offs = sl.in.as<uint64_t>();
+  uint8_t* d_bytes = sl.in.as<uint8_t>() + offs_bytes;
+  uint64_t* d_counts = sl.out.as<uint64_t>();
+  uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
+  CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, sl.stream));
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  const uint32_t saved = idx->instr_mask;
+  idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
+  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, sl.stream);
+  idx->instr_mask = saved;
+  if (rc) return rc;
+  CSFM_CUDA(cudaMemcpyAsync(counts, d_counts, npat * 8, cudaMemcpyDeviceToHost, sl.stream));
+  if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, sl.stream));
+  idx->stats.h2d_bytes = offs_bytes + nbytes;
+  idx->stats.d2h_bytes = npat * 8 * (sp_ep ? 3 : 1);
+  return CSFM_OK;
+}
+
+int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket) {
+  if (!idx || ticket == 0) return fail(CSFM_ERR_INVALID, "bad ticket");
+  DeviceGuard g(idx->device);
+  cudaStream_t st = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    csfm_index::AsyncSlot& sl = idx->async_slot[ticket % CSFM_ASYNC_SLOTS];
+    if (sl.ticket != ticket) return CSFM_OK;  // already waited on (or recycled, which waited on it)
+    st = sl.stream;
+  }
+  CSFM_CUDA(cudaStreamSynchronize(st));
+  std::lock_guard<std::mutex> lk(idx->mu);
+  csfm_index::AsyncSlot& sl = idx->async_slot[ticket % CSFM_ASYNC_SLOTS];
+  if (sl.ticket == ticket) sl.ticket = 0;
+  return CSFM_OK;
 }
 
 int csfm_locate_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,

@@ -54,6 +54,12 @@ struct csfm_index {
 
   cudaStream_t stream = nullptr;  // used by the host-pointer API
   cudaStream_t aux_stream[2] = {nullptr, nullptr};  // slice pipeline of large host-pointer batches
+  struct AsyncSlot {  // csfm_count_batch_submit / _wait
+    cudaStream_t stream = nullptr;
+    csfm::DeviceBuffer in, out;
+    uint64_t ticket = 0;  // ticket currently occupying the slot (0 = free)
+  } async_slot[CSFM_ASYNC_SLOTS];
+  uint64_t next_ticket = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
   unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators

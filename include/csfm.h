@@ -149,6 +149,17 @@ CSFM_API int csfm_from_host_blob(const void* blob, uint64_t bytes, int device, c
  * executed step, (0,0) for empty patterns and empty results. */
 CSFM_API int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs,
                               uint64_t npat, uint64_t* counts, uint64_t* sp_ep);
+/* Asynchronous form for streaming callers: submit enqueues host->device copies, the kernel and
+ * the device->host copy of one batch on one of CSFM_ASYNC_SLOTS internal streams and returns a
+ * ticket; wait blocks until that batch's results are in `counts` / `sp_ep`. Keeping two or three
+ * batches in flight overlaps the PCIe copies of one batch with the kernel of another. The host
+ * buffers must stay valid (and should be pinned, csfm_host_alloc) until the ticket is waited on;
+ * a slot is reused after CSFM_ASYNC_SLOTS submits (submit waits for it if still busy). */
+#define CSFM_ASYNC_SLOTS 3
+CSFM_API int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs,
+                                     uint64_t npat, uint64_t* counts, uint64_t* sp_ep,
+                                     uint64_t* ticket);
+CSFM_API int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket);
 CSFM_API int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes,
                                      const uint64_t* d_offs, uint64_t npat, uint64_t* d_counts,
                                      uint64_t* d_sp_ep, void* stream);

@@ -329,3 +329,28 @@ def test_tma_staged_count_variant(fm, monkeypatch):
         offs, pos, status = idx.locate_batch(d, o, limit=11)
         ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=11)
         assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
+
+
+def test_async_submit_wait(fm):
+    """csfm_count_batch_submit/_wait: several batches in flight on internal streams, pinned buffers."""
+    import torch
+    rng = np.random.default_rng(31)
+    text, alpha = _rand_text(rng, 100_000, 4, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16))
+    orc = oracle.OracleIndex(text, stride=16)
+    jobs = []
+    for k in range(7):
+        pats = _mixed_patterns(rng, text, alpha, 5000 + 37 * k, 18)
+        d, o = fm.pack_patterns(pats)
+        hb = torch.from_numpy(d.copy()).pin_memory() if d.size else torch.zeros(1, dtype=torch.uint8).pin_memory()
+        ho = torch.from_numpy(o.astype(np.int64)).pin_memory()
+        hc = torch.zeros(o.size - 1, dtype=torch.int64).pin_memory()
+        hs = torch.zeros(2 * (o.size - 1), dtype=torch.int64).pin_memory()
+        t = idx.count_batch_submit(hb.data_ptr(), ho.data_ptr(), o.size - 1, hc.data_ptr(), hs.data_ptr())
+        jobs.append((t, d, o, hb, ho, hc, hs))
+    for t, d, o, hb, ho, hc, hs in reversed(jobs):  # any order
+        idx.count_batch_wait(t)
+        idx.count_batch_wait(t)  # idempotent
+        oc, ose = orc.count_batch(d, o)
+        assert (hc.numpy().astype(np.uint64) == oc).all()
+        assert (hs.numpy().astype(np.uint64).reshape(-1, 2) == ose).all()
