@@ -491,7 +491,9 @@ def run_engine(args, rank, world, local_rank):
             traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_name = ("count2_tma_kernel" if os.environ.get("CSFM_PATTERN_STAGING") == "tma" else "count2_kernel") \
+        if int(info.layout) == 2 else "count_kernel"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
                 "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
@@ -499,7 +501,15 @@ def run_engine(args, rank, world, local_rank):
                 "kmer_k": int(info.kmer_k),
                 "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
                 "note": "duration per launch = CUDA events on the launching stream around each step "
-                        "(32-byte cursor memset + count_kernel)"}
+                        "(32-byte cursor memset + the count kernel). achieved = algorithmic bytes (rank steps x 2 x L x "
+                        "line + table lookups x 128 B) / duration; sp and ep share a line after ~4 steps, so the real "
+                        "DRAM traffic (`traffic`, ncu) is about half of that and frac can exceed 1"}
+    if traffic:
+        # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)
+        roofline["dram_gbs_from_traffic"] = traffic / (total_ms / args.steps / 1e3) / 1e9
+        roofline["line_fetches_per_s"] = traffic / 128 / (total_ms / args.steps / 1e3)
+        roofline["random_fetch_ceiling_lines_per_s"] = 37.3e9
+        roofline["frac_of_random_fetch_ceiling"] = roofline["line_fetches_per_s"] / 37.3e9
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, checked vs the GPU
     cpu = None
