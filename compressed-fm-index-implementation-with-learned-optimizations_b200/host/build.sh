@@ -6,8 +6,8 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/libcs_b200.so"
 CXX=/usr/bin/g++
 [[ -x "$CXX" ]] || CXX=g++
-if [[ -f "$OUT" && "$OUT" -nt "$HERE/src/api/fm_index.cpp" && "$OUT" -nt "$HERE/src/api/fm_index.hpp" && "$OUT" -nt "$HERE/../libcsfm.so" && "${1:-}" != "-f" ]]; then
+if [[ -f "$OUT" && "$OUT" -nt "$HERE/src/api/fm_index.cpp" && "$OUT" -nt "$HERE/src/serialization/csidx.cpp" && "$OUT" -nt "$HERE/src/serialization/csidx.hpp" && "$OUT" -nt "$HERE/src/api/fm_index.hpp" && "$OUT" -nt "$HERE/../libcsfm.so" && "${1:-}" != "-f" ]]; then
   exit 0
 fi
-"$CXX" -std=c++20 -O2 -fPIC -Wall -Wextra -shared -o "$OUT" "$HERE/src/api/fm_index.cpp" \
+"$CXX" -std=c++20 -O2 -fPIC -Wall -Wextra -shared -o "$OUT" "$HERE/src/api/fm_index.cpp" "$HERE/src/serialization/csidx.cpp" \
   -L"$HERE/.." -lcsfm -Wl,-rpath,'$ORIGIN/..'

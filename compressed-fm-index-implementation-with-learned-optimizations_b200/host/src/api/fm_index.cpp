@@ -7,6 +7,7 @@
 #include <stdexcept>
 
 #include "../../../../include/csfm.h"
+#include "../serialization/csidx.hpp"
 #include "../util/timer.hpp"
 
 namespace cs {
@@ -130,6 +131,49 @@ std::vector<uint64_t> FMIndex::locate(std::string_view pattern, size_t limit) co
   if (r.status[0] == CSFM_Q_SSA_OOB)
     throw std::runtime_error("locate: SSA sample index out of range");  // fm_index.cpp:143
   return std::move(r.positions);
+}
+
+void FMIndex::save(const std::string& path) const {
+  if (!handle_) throw std::runtime_error("save: index not built");
+  csfm_index_info info;
+  if (csfm_info(handle_.get(), &info) != CSFM_OK) throw_last("save");
+  CsidxSections s;
+  s.text_len = meta_.n;
+  if (text_) {
+    s.has_text = true;
+    s.text = *text_;
+  }
+  s.bwt.resize(info.n);
+  if (info.n && csfm_extract_bwt(handle_.get(), s.bwt.data()) != CSFM_OK) throw_last("save");
+  s.c_array.resize(257);
+  if (csfm_get_C(handle_.get(), s.c_array.data()) != CSFM_OK) throw_last("save");
+  s.has_ssa = true;
+  s.ssa_stride = info.ssa_stride;
+  s.ssa.resize(info.nsamp);
+  if (info.nsamp && csfm_get_ssa(handle_.get(), s.ssa.data()) != CSFM_OK) throw_last("save");
+  s.device_blob.resize(info.blob_bytes);
+  if (csfm_blob_to_host(handle_.get(), s.device_blob.data(), s.device_blob.size()) != CSFM_OK) throw_last("save");
+  write_csidx(path, s);
+}
+
+FMIndex FMIndex::load(const std::string& path) {
+  CsidxSections s = read_csidx(path);
+  FMIndex idx;
+  csfm_index* h = nullptr;
+  if (!s.device_blob.empty()) {
+    if (csfm_from_host_blob(s.device_blob.data(), s.device_blob.size(), default_device(), &h) != CSFM_OK) throw_last("load");
+  } else {
+    if (!s.has_ssa || s.ssa_stride == 0) throw std::runtime_error("load: file has neither a device blob nor an SSA section");
+    if (csfm_build_from_parts(s.bwt.data(), s.bwt.size(), s.ssa.data(), s.ssa.size(), s.ssa_stride, default_device(),
+                              CSFM_BUILD_DEFAULT, &h) != CSFM_OK)
+      throw_last("load");
+  }
+  idx.handle_ = std::shared_ptr<csfm_index>(h, [](csfm_index* x) { csfm_destroy(x); });
+  csfm_index_info info;
+  if (csfm_info(h, &info) != CSFM_OK) throw_last("load");
+  idx.meta_.n = info.n;
+  if (s.has_text) idx.text_ = std::make_shared<const std::string>(std::move(s.text));
+  return idx;
 }
 
 std::string FMIndex::extract(uint64_t p, uint64_t len) const {

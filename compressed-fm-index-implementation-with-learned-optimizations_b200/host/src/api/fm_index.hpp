@@ -56,6 +56,13 @@ public:
                    uint64_t* sp_ep = nullptr) const;
   LocateBatch locate_batch(const std::vector<std::string_view>& patterns, size_t limit = 100000) const;
 
+  // ---- persistence (new): the reference's .csidx container (src/serialization/serialization.hpp)
+  /// Writes TEXT, BWT, C_ARRAY, SSA and the device-resident index blob (host/src/serialization/csidx.hpp).
+  void save(const std::string& path) const;
+  /// Loads a file written by save(): one read + one host->device copy, no rebuild. Files without
+  /// the device blob are rebuilt from their BWT + SSA sections.
+  static FMIndex load(const std::string& path);
+
   // ---- introspection / placement ------------------------------------------------------------
   uint64_t size() const { return meta_.n; }
   int device() const;

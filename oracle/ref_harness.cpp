@@ -11,7 +11,9 @@
 // same order and with the same reference helpers as FMIndex::build_from_text
 // (src/api/fm_index.cpp:16-69), from a suffix array supplied by the caller, and then call the
 // reference's count()/locate() verbatim. This TU is compiled with -fno-access-control for that.
+#include <cstring>  // the reference's serialization.hpp uses memset/memcpy without it
 #include "api/fm_index.hpp"
+#include "serialization/serialization.hpp"
 #include "core/sais.hpp"
 #include "core/bwt.hpp"
 
@@ -274,6 +276,61 @@ uint64_t csref_bv_rank1(void* b, uint64_t i) { return static_cast<cs::BitVector*
 uint64_t csref_bv_rank0(void* b, uint64_t i) { return static_cast<cs::BitVector*>(b)->rank0(i); }
 uint8_t csref_bv_get(void* b, uint64_t i) { return static_cast<cs::BitVector*>(b)->get(i); }
 uint64_t csref_bv_size(void* b) { return static_cast<cs::BitVector*>(b)->size(); }
+
+// ---- cs::IndexReader / cs::IndexWriter (src/serialization/serialization.cpp) ----------------------
+// The reader is the format oracle for .csidx files. The writer is only usable when no padding is
+// ever needed (its align_to never terminates otherwise, serialization.cpp:44-54).
+void* csref_reader_open(const char* path) {
+  try {
+    return new cs::IndexReader(path);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void csref_reader_close(void* r) { delete static_cast<cs::IndexReader*>(r); }
+int csref_reader_header(void* r, uint32_t* flags, uint64_t* text_len, uint64_t* offsets8) {
+  const cs::IndexHeader* h = static_cast<cs::IndexReader*>(r)->header();
+  if (!h || !h->is_valid()) return 1;
+  *flags = h->flags;
+  *text_len = h->text_len;
+  std::memcpy(offsets8, h->offsets, 64);
+  return 0;
+}
+const void* csref_reader_section(void* r, int which, uint64_t* count, uint32_t* stride) {
+  auto* rd = static_cast<cs::IndexReader*>(r);
+  size_t n = 0;
+  uint32_t st = 0;
+  const void* p = nullptr;
+  switch (which) {
+    case 1: p = rd->get_text(&n); break;
+    case 2: p = rd->get_bwt(&n); break;
+    case 3: p = rd->get_c_array(&n); break;
+    case 4: p = rd->get_ssa(&n, &st); break;
+    case 5: p = rd->get_wavelet(&n); break;
+    case 6: p = rd->get_veb_layout(&n); break;
+    default: break;
+  }
+  *count = n;
+  if (stride) *stride = st;
+  return p;
+}
+// header + TEXT + BWT + C_ARRAY with the reference writer (caller guarantees no padding is needed)
+int csref_writer_simple(const char* path, uint32_t flags, const uint8_t* text, uint64_t ntext, const uint8_t* bwt,
+                        uint64_t nbwt, const uint32_t* c, uint64_t nc) {
+  try {
+    cs::IndexWriter w(path);
+    w.write_header(flags, ntext);
+    w.write_text(std::string(reinterpret_cast<const char*>(text), ntext));
+    w.write_bwt(std::vector<uint8_t>(bwt, bwt + nbwt));
+    w.write_c_array(std::vector<uint32_t>(c, c + nc));
+    w.finalize();
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
 
 int csref_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 

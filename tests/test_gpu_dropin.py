@@ -64,7 +64,8 @@ def test_cpp_batch_api(tmp_path):
 #include "api/fm_index.hpp"
 #include <cassert>
 #include <iostream>
-int main() {
+int main(int argc, char** argv) {
+  (void)argc;
   std::string text;
   for (int i = 0; i < 5000; ++i) text += "the quick brown fox jumps over the lazy dog "[(i * 7 + i / 3) % 44];
   text += '$';
@@ -91,6 +92,16 @@ int main() {
   threw = false;
   try { bad.locate("a"); } catch (const std::runtime_error& e) { threw = std::string(e.what()) == "locate: LF walk exceeded text length"; }
   assert(threw);
+  // .csidx round trip: save -> load (one read + one host->device copy) -> same answers
+  const std::string path = std::string(argv[1]) + "/index.csidx";
+  idx.save(path);
+  cs::FMIndex back = cs::FMIndex::load(path);
+  assert(back.size() == idx.size());
+  auto counts2 = back.count_batch(pats);
+  assert(counts2 == counts);
+  auto loc2 = back.locate_batch(views, 17);
+  assert(loc2.offsets == loc.offsets && loc2.positions == loc.positions && loc2.status == loc.status);
+  assert(back.extract(4, 5) == text.substr(4, 5));
   std::cout << "ok " << counts[0] << "\n";
   return 0;
 }
@@ -100,6 +111,6 @@ int main() {
     subprocess.run([cxx, "-std=c++20", "-O1", "-I" + os.path.join(pkg, "host", "src"), "-o", str(exe), str(src),
                     "-L" + os.path.join(pkg, "host"), "-lcs_b200", "-L" + pkg, "-lcsfm",
                     "-Wl,-rpath," + os.path.join(pkg, "host"), "-Wl,-rpath," + pkg], check=True)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-800:]
     assert r.stdout.startswith("ok ")
