@@ -1,0 +1,58 @@
+"""GPU property tests (hypothesis): arbitrary small texts over arbitrary alphabets, with and without
+a terminator, arbitrary strides and limits — the engine must agree with the oracle bit for bit,
+including the reference's quirks (cyclic over-count, non-terminating LF walks -> status 1)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fm():
+    import csfm_b200
+    csfm_b200.lib()
+    return csfm_b200
+
+
+texts = st.one_of(
+    st.binary(min_size=1, max_size=600),
+    st.lists(st.sampled_from(list(b"ACGT")), min_size=1, max_size=900).map(bytes),
+    st.lists(st.sampled_from([0, 1, 255]), min_size=1, max_size=300).map(bytes),
+    st.builds(lambda unit, reps, tail: unit * reps + tail, st.binary(min_size=1, max_size=5), st.integers(1, 150),
+              st.binary(max_size=3)),
+)
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(text=texts, stride=st.sampled_from([1, 2, 3, 4, 7, 32, 1000]), limit=st.sampled_from([1, 2, 5, 100000]),
+       flags=st.sampled_from([0, 1, 4, 5, 8]), seed=st.integers(0, 2**31 - 1), terminate=st.booleans())
+def test_engine_equals_oracle(fm, text, stride, limit, flags, seed, terminate):
+    if terminate:
+        text = text + b"\x00"
+    t = np.frombuffer(text, np.uint8)
+    idx = fm.FMIndex.build_from_text(t, fm.BuildParams(ssa_stride=stride), flags=flags | fm.BUILD_KEEP_SA)
+    orc = oracle.OracleIndex(t, stride=stride)
+    assert (idx.sa() == orc.sa).all()
+    assert (idx.bwt() == orc.bwt).all() and (idx.ssa() == orc.ssa).all() and (idx.C_array() == orc.C).all()
+    rng = np.random.default_rng(seed)
+    pats = [b""]
+    for _ in range(40):
+        m = int(rng.integers(1, 9))
+        if rng.random() < 0.7 and t.size > m:
+            s = int(rng.integers(0, t.size - m + 1))
+            pats.append(t[s:s + m].tobytes())
+        else:
+            pats.append(rng.integers(0, 256, m, dtype=np.uint8).tobytes())
+    pats.append(text[-min(len(text), 40):])
+    d, o = fm.pack_patterns(pats)
+    counts, sp_ep = idx.count_batch(d, o, want_intervals=True)
+    oc, ose = orc.count_batch(d, o)
+    assert (counts == oc).all() and (sp_ep == ose).all()
+    offs, pos, status = idx.locate_batch(d, o, limit=limit)
+    ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=limit)
+    assert (offs == ooffs).all() and (status == ostatus).all()
+    ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
+    assert (pos[ok] == opos[ok]).all()
