@@ -69,6 +69,7 @@ SIGNATURES = {
     "csfm_get_C": (C.c_int, [_vp, _vp]),
     "csfm_get_ssa": (C.c_int, [_vp, _vp]),
     "csfm_get_sa": (C.c_int, [_vp, _vp]),
+    "csfm_sa_device": (C.c_int, [_vp, C.POINTER(_vp)]),
     "csfm_release_sa": (C.c_int, [_vp]),
     "csfm_extract_bwt": (C.c_int, [_vp, _vp]),
     "csfm_blob": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
@@ -234,6 +235,11 @@ class FMIndex:
         out = np.zeros(max(1, self.n), np.uint32)
         _check(lib().csfm_get_sa(self._h, _np_ptr(out)))
         return out[: self.n]
+
+    def sa_device_ptr(self) -> int:
+        p = _vp()
+        _check(lib().csfm_sa_device(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     def release_sa(self):
         _check(lib().csfm_release_sa(self._h))

@@ -230,6 +230,13 @@ int csfm_get_sa(const csfm_index* idx, uint32_t* out) {
   return CSFM_OK;
 }
 
+int csfm_sa_device(const csfm_index* idx, const uint32_t** d_sa) {
+  if (!idx || !d_sa) return fail(CSFM_ERR_INVALID, "null argument");
+  if (idx->h.n && !idx->d_sa) return fail(CSFM_ERR_INVALID, "suffix array not resident (build with CSFM_BUILD_KEEP_SA)");
+  *d_sa = idx->d_sa;
+  return CSFM_OK;
+}
+
 int csfm_release_sa(csfm_index* idx) {
   if (!idx) return fail(CSFM_ERR_INVALID, "null argument");
   DeviceGuard g(idx->device);

@@ -140,6 +140,45 @@ def _umod_torch_big(z, m: int):
     return r
 
 
+def certify_sa_torch(text, sa_ptr: int, n: int, chunk: int = 1 << 27) -> dict:
+    """O(n) certificate, in plain torch on the GPU, that the uint32 array at device pointer `sa_ptr`
+    is THE suffix array of `text` in the reference's order (unsigned bytes, a proper prefix first):
+    it is a permutation, and for neighbours a = SA[i], b = SA[i+1]: T[a] < T[b], or T[a] == T[b] and
+    the suffix after a sorts before the suffix after b (a+1 == n counts as smallest)."""
+    import torch
+    dev = text.device
+
+    class _Mem:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    raw = torch.as_tensor(_Mem(sa_ptr, 4 * n), device=dev)
+
+    def sa_chunk(lo, hi):  # uint32 -> int64
+        return raw[4 * lo:4 * hi].view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+
+    isa = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        s = sa_chunk(lo, hi)
+        if int(s.max()) >= n:
+            return {"ok": False, "why": "value out of range"}
+        isa[s] = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    if int(isa.min()) < 0:
+        return {"ok": False, "why": "not a permutation"}
+    bad = 0
+    for lo in range(0, n - 1, chunk):
+        hi = min(n - 1, lo + chunk)
+        a, b = sa_chunk(lo, hi), sa_chunk(lo + 1, hi + 1)
+        ta, tb = text[a], text[b]
+        a1, b1 = a + 1, b + 1
+        ra = torch.where(a1 < n, isa[torch.clamp(a1, max=n - 1)], torch.full_like(a, -1))
+        rb = torch.where(b1 < n, isa[torch.clamp(b1, max=n - 1)], torch.full_like(b, -1))
+        ok = (ta < tb) | ((ta == tb) & (ra < rb))
+        bad += int((~ok).sum())
+    return {"ok": bad == 0, "violations": bad}
+
+
 def random_patterns_np(alphabet: bytes, npat: int, length: int, seed: int):
     """Uniform random strings over `alphabet` (mostly misses: die after ~log_sigma(n) steps)."""
     idx = np.arange(npat * length, dtype=np.uint64)

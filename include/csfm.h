@@ -129,6 +129,8 @@ CSFM_API int csfm_info(const csfm_index* idx, csfm_index_info* out);
 CSFM_API int csfm_get_C(const csfm_index* idx, uint32_t C[257]);           /* fm_index.cpp:36-47 */
 CSFM_API int csfm_get_ssa(const csfm_index* idx, uint32_t* out /*nsamp*/); /* fm_index.cpp:57-65 */
 CSFM_API int csfm_get_sa(const csfm_index* idx, uint32_t* out /*n*/);      /* needs KEEP_SA */
+/* Device pointer of the resident suffix array (n x uint32), for on-device certification. */
+CSFM_API int csfm_sa_device(const csfm_index* idx, const uint32_t** d_sa);
 CSFM_API int csfm_release_sa(csfm_index* idx);
 /* BWT re-derived from the wavelet matrix by an access kernel (wavelet.cpp:102-128). */
 CSFM_API int csfm_extract_bwt(const csfm_index* idx, uint8_t* out /*n*/);
