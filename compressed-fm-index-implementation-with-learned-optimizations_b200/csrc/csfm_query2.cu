@@ -53,7 +53,7 @@ __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32
 // ------------------------------------------------------------------------------------------
 // Default variant: pattern offsets and bytes are read straight from global memory (two dependent
 // loads when a sub-warp starts a pattern, then a one-step byte prefetch).
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, 8)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
   load_tables(tb, iv.hdr);
@@ -480,7 +480,7 @@ __device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict_
 // ------------------------------------------------------------------------------------------
 // locate: rows -> text positions (fm_index.cpp:125-153, LF of fm_index.hpp:62-66)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, 8)
 walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
   __shared__ Tables tb;
   load_tables(tb, iv.hdr);
