@@ -320,6 +320,9 @@ int index_finish_handle(csfm_index* idx) {
   v.stride = h.stride;
   v.nsamp = (uint32_t)h.nsamp;
   v.layout = h.layout;
+  v.stride_shift = 32;
+  if ((h.stride & (h.stride - 1)) == 0)
+    for (v.stride_shift = 0; (1u << v.stride_shift) < h.stride; ++v.stride_shift) {}
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;

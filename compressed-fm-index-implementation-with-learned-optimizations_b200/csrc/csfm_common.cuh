@@ -102,7 +102,7 @@ struct IndexView {
   uint32_t stride;
   uint32_t nsamp;
   uint32_t layout;
-  uint32_t pad;
+  uint32_t stride_shift;  // log2(stride) when the stride is a power of two, else 32
   uint32_t zeros[kMaxLevels];
 };
 
@@ -201,6 +201,15 @@ __device__ __forceinline__ uint32_t chunk_symbol(const Chunk32& k, uint32_t off)
   const uint32_t s = off & 31u;
   const uint32_t w = pick4(k.p0, k.p1, k.p2, k.p3, s);
   return (w >> (4u * (s >> 2))) & 15u;
+}
+
+// SA rows are sampled at multiples of the stride (fm_index.cpp:57-65): no hardware divide for the
+// usual power-of-two strides.
+__device__ __forceinline__ bool row_is_sampled(const IndexView& iv, uint32_t row) {
+  return iv.stride_shift < 32 ? (row & (iv.stride - 1u)) == 0u : row % iv.stride == 0u;
+}
+__device__ __forceinline__ uint32_t sample_index(const IndexView& iv, uint32_t row) {
+  return iv.stride_shift < 32 ? row >> iv.stride_shift : row / iv.stride;
 }
 
 __device__ __forceinline__ uint32_t group4_sum(uint32_t v) {

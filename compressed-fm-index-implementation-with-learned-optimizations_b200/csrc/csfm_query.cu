@@ -190,7 +190,7 @@ walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkAr
     active = false;
   };
   auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]
-    const uint32_t k = row / iv.stride;
+    const uint32_t k = sample_index(iv, row);
     if (k >= iv.nsamp) {  // fm_index.cpp:141-146 (unreachable for a consistent index)
       fail_walk((int)CSFM_Q_SSA_OOB);
       return;
@@ -210,7 +210,7 @@ walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkAr
       start = (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
-      if (start % iv.stride == 0) {
+      if (row_is_sampled(iv, start)) {
         emit(start);
       } else {
         p = start;
@@ -243,7 +243,7 @@ walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkAr
         const uint32_t row = tb.base_by_code[code] + p;
         ++steps;
         ++my_lf;
-        if (row % iv.stride == 0) {
+        if (row_is_sampled(iv, row)) {
           emit(row);
         } else if (row == start || steps >= iv.n) {
           // LF is a permutation: back at the start without meeting a sampled row means the

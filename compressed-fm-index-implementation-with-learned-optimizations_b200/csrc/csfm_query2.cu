@@ -510,7 +510,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
     active = false;
   };
   auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]
-    const uint32_t k = row / iv.stride;
+    const uint32_t k = sample_index(iv, row);
     if (k >= iv.nsamp) {  // fm_index.cpp:141-146 (unreachable for a consistent index)
       fail_walk((int)CSFM_Q_SSA_OOB);
       return;
@@ -531,7 +531,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
       steps = 0;
       active = true;
       p = start;
-      if (start % iv.stride == 0) emit(start);
+      if (row_is_sampled(iv, start)) emit(start);
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
@@ -547,7 +547,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
       const uint32_t row = tb.base_by_code[code] + r;
       ++steps;
       ++my_lf;
-      if (row % iv.stride == 0) {
+      if (row_is_sampled(iv, row)) {
         emit(row);
       } else if (row == start || steps >= iv.n) {
         // LF is a permutation: back at the start without meeting a sampled row means the
