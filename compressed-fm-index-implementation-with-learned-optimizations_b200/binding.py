@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(HERE, "libcsfm.so")
 
 CSFM_OK, CSFM_ERR_INVALID, CSFM_ERR_CUDA, CSFM_ERR_NOMEM, CSFM_ERR_TOO_LARGE, CSFM_ERR_CAPACITY, CSFM_ERR_FORMAT = range(7)
 Q_OK, Q_LF_WALK_EXCEEDED, Q_SSA_OOB = 0, 1, 2
-BUILD_DEFAULT, BUILD_NO_COMPACT, BUILD_KEEP_SA, BUILD_LAYOUT_BINARY64, BUILD_NO_KMER_TABLE = 0, 1, 2, 4, 8
+BUILD_DEFAULT, BUILD_NO_COMPACT, BUILD_KEEP_SA, BUILD_LAYOUT_BINARY64, BUILD_NO_KMER_TABLE, BUILD_NO_TEXT_CHECK = 0, 1, 2, 4, 8, 16
 
 LF_WALK_MESSAGE = "locate: LF walk exceeded text length"  # fm_index.cpp:137
 
@@ -47,13 +47,13 @@ class IndexInfo(C.Structure):
     _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("levels", C.c_uint32), ("ssa_stride", C.c_uint32),
                 ("device", C.c_uint32), ("nsamp", C.c_uint64), ("blocks_per_level", C.c_uint64),
                 ("blob_bytes", C.c_uint64), ("has_sa", C.c_uint32), ("layout", C.c_uint32), ("line_bytes", C.c_uint32),
-                ("kmer_k", C.c_uint32)]
+                ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class CallStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("search_steps", C.c_uint64), ("lf_steps", C.c_uint64), ("kernel_ms", C.c_float),
-                ("table_lookups", C.c_uint32)]
+                ("table_lookups", C.c_uint32), ("text_checks", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 # name -> (restype, argtypes): every symbol include/csfm.h declares

@@ -93,17 +93,20 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
   uint8_t* d_bwt = nullptr;
   uint32_t *d_ssa = nullptr, *d_sa = nullptr;
   uint64_t nsamp = 0;
-  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp,
-                           (flags & CSFM_BUILD_KEEP_SA) ? &d_sa : nullptr);
+  const bool want_sa = (flags & CSFM_BUILD_KEEP_SA) || !((flags & CSFM_BUILD_NO_TEXT_CHECK) || (flags & CSFM_BUILD_LAYOUT_BINARY64));
+  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp, want_sa ? &d_sa : nullptr);
   if (rc) return rc;
-  rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, stride, device, flags, out);
+  rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, stride, device, flags, out, d_text, d_sa);
   cudaFree(d_bwt);
   cudaFree(d_ssa);
   if (rc) {
     cudaFree(d_sa);
     return rc;
   }
-  (*out)->d_sa = d_sa;
+  if (flags & CSFM_BUILD_KEEP_SA)
+    (*out)->d_sa = d_sa;
+  else
+    cudaFree(d_sa);
   return CSFM_OK;
 }
 
@@ -205,6 +208,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->layout = idx->h.layout;
   out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;
   out->kmer_k = idx->view.kmer_k;
+  out->text_check = idx->view.text != nullptr;
   return CSFM_OK;
 }
 
@@ -286,6 +290,11 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
       h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * line_bytes ||
       h.nsamp != (h.n + h.stride - 1) / h.stride)
     return fail(CSFM_ERR_FORMAT, "inconsistent blob header");
+  if (h.off_text) {
+    if (!nib || h.n < 2 || h.dense_shift > 16 || h.off_text % 16 || h.off_text + h.n + 64 > h.off_dense ||
+        h.off_dense + (((h.n - 1) >> h.dense_shift) + 1) * 4 > h.total_bytes || h.off_text < h.off_ssa + h.nsamp * 4)
+      return fail(CSFM_ERR_FORMAT, "inconsistent text sections in blob header");
+  }
   if (h.kmer_k) {
     uint64_t entries = 1;
     for (uint32_t i = 0; i < h.kmer_k && entries <= (1ull << 40); ++i) entries *= h.kmer_radix;
@@ -354,6 +363,7 @@ static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
     } else {
       idx->stats.search_steps = hp[8];
       idx->stats.table_lookups = (uint32_t)hp[10];
+      idx->stats.text_checks = (uint32_t)hp[11];
     }
   }
   if (idx->instr_mask & 2u) {
@@ -570,6 +580,7 @@ int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out) {
   if (idx->instr_mask & 1u) {
     if (!out->search_steps) out->search_steps = hp[8];
     if (!out->table_lookups) out->table_lookups = (uint32_t)hp[10];
+    if (!out->text_checks) out->text_checks = (uint32_t)hp[11];
     if (!out->lf_steps) out->lf_steps = hp[9];
   }
   if ((idx->instr_mask & 2u) && out->kernel_ms == 0.f) {

@@ -326,6 +326,10 @@ int index_finish_handle(csfm_index* idx) {
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
+  v.text = h.off_text ? idx->d_blob + h.off_text : nullptr;
+  v.dense = h.off_text ? reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_dense) : nullptr;
+  v.dense_shift = h.dense_shift;
+  if (std::getenv("CSFM_NO_TEXT_CHECK")) v.text = nullptr;  // experiment knob: ignore the sections
   if (std::getenv("CSFM_NO_KMER_TABLE")) {  // experiment knob: ignore a table that is present
     v.kmer = nullptr;
     v.kmer_k = 0;
@@ -343,7 +347,8 @@ int index_finish_handle(csfm_index* idx) {
 }
 
 int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ssa, uint64_t nsamp,
-                          uint32_t stride, int device, uint32_t flags, csfm_index** out) {
+                          uint32_t stride, int device, uint32_t flags, csfm_index** out,
+                          const uint8_t* d_text, const uint32_t* d_sa) {
   if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
   if (stride == 0) return fail(CSFM_ERR_INVALID, "ssa_stride must be > 0");
   cudaStream_t st = nullptr;  // construction runs on the legacy default stream of the device
@@ -391,6 +396,20 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
       h.kmer_radix = (uint32_t)radix;
       h.off_kmer = h.total_bytes;
       h.total_bytes = align_up(h.off_kmer + entries * 8, 256);
+    }
+  }
+  // Text-verification shortcut: needs the text and its suffix array, and a text whose last byte
+  // is unique and the smallest present (then row r <-> suffix SA[r] and LF(r) <-> SA[r]-1 cyclically,
+  // so "keep stepping from a one-row interval" equals "compare with the text"; without such a
+  // terminator the reference's BWT is not a rotation BWT and the shortcut would change results).
+  if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK)) {
+    uint8_t last = 0;
+    cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
+    if (e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0) {
+      h.dense_shift = 0;  // the full suffix array: no extra steps to reach a sampled row
+      h.off_text = h.total_bytes;
+      h.off_dense = align_up(h.off_text + n + 64, 256);
+      h.total_bytes = align_up(h.off_dense + (((n - 1) >> h.dense_shift) + 1) * 4, 256);
     }
   }
 
@@ -475,9 +494,14 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
       }
     }
   }
-  // 3) SA samples + header
+  // 3) SA samples (+ text and suffix array for the verification shortcut) + header
   if (nsamp)
     BUILD_CUDA(cudaMemcpyAsync(idx->d_blob + h.off_ssa, d_ssa, nsamp * 4, cudaMemcpyDeviceToDevice, st));
+  if (h.off_text) {
+    BUILD_CUDA(cudaMemcpyAsync(idx->d_blob + h.off_text, d_text, n, cudaMemcpyDeviceToDevice, st));
+    BUILD_CUDA(cudaMemsetAsync(idx->d_blob + h.off_text + n, 0, h.off_dense - (h.off_text + n), st));
+    BUILD_CUDA(cudaMemcpyAsync(idx->d_blob + h.off_dense, d_sa, n * 4, cudaMemcpyDeviceToDevice, st));  // dense_shift == 0
+  }
   {
     std::vector<uint8_t> hdr(kHeaderBytes, 0);
     std::memcpy(hdr.data(), &h, sizeof h);

@@ -73,7 +73,13 @@ struct BlobHeader {
   uint32_t kmer_k;             // 0 = no table
   uint32_t kmer_radix;         // number of compact codes (sigma, or 256 with NO_COMPACT)
   uint64_t off_kmer;           // byte offset of the table (uint2 entries)
-  uint32_t reserved0[10];
+  // text-verification shortcut (layout 2, texts with a unique smallest last byte): the text and
+  // SA[k << dense_shift] for every k, so that a query whose interval has shrunk to ONE row can
+  // finish by comparing its remaining characters with the text instead of stepping through them.
+  uint64_t off_text;           // 0 = absent; n bytes + 64 bytes of padding, 16-byte aligned
+  uint64_t off_dense;          // u32 samples
+  uint32_t dense_shift;        // samples at rows that are multiples of 1 << dense_shift
+  uint32_t reserved0[5];
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
@@ -94,6 +100,8 @@ struct IndexView {
   const uint32_t* ssa;
   const BlobHeader* hdr;  // device pointer (tables are staged to shared memory per CTA)
   const uint2* kmer;      // k-mer jump table or nullptr
+  const uint8_t* text;    // text for the verification shortcut or nullptr
+  const uint32_t* dense;  // SA[k << dense_shift]
   uint32_t kmer_k;
   uint32_t kmer_radix;
   uint64_t level_stride;
@@ -103,6 +111,8 @@ struct IndexView {
   uint32_t nsamp;
   uint32_t layout;
   uint32_t stride_shift;  // log2(stride) when the stride is a power of two, else 32
+  uint32_t dense_shift;
+  uint32_t pad1;
   uint32_t zeros[kMaxLevels];
 };
 

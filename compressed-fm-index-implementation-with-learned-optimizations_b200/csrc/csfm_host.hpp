@@ -77,8 +77,11 @@ namespace csfm {
 constexpr uint32_t kCounterSlots = 256;  // each slot = 4 x u64
 
 // csfm_build.cu
+// d_text / d_sa (both nullable): when given and the text ends in a unique smallest byte, they are
+// copied into the blob for the verification shortcut.
 int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ssa, uint64_t nsamp,
-                          uint32_t stride, int device, uint32_t flags, csfm_index** out);
+                          uint32_t stride, int device, uint32_t flags, csfm_index** out,
+                          const uint8_t* d_text = nullptr, const uint32_t* d_sa = nullptr);
 int index_finish_handle(csfm_index* idx);  // fills view/stream/workspace after d_blob + h are set
 int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: fills the table section
 // csfm_sa.cu

@@ -100,6 +100,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // Orders earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that occupy no registers -----------
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Text-verification shortcut: at most kVerifyMax remaining characters are compared with the text
+// in one go; the two windows (text, pattern) are staged in a per-sub-warp slot as aligned 16-byte
+// chunks (a window of 32 unaligned bytes spans at most three of them).
+constexpr uint32_t kVerifyMax = 32;
+struct alignas(16) VerifySlot {
+  uint8_t t[48];
+  uint8_t p[48];
+};
+
 constexpr uint32_t kStageBytes = 2048;  // pattern bytes staged per warp chunk (32 patterns)
 constexpr uint32_t kPrivBytes = 64;     // private slot per sub-warp for the pattern it is working on
 

@@ -66,12 +66,23 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const uint32_t kk = iv.kmer_k;  // 0 = no jump table
   WarpQueue wq;
 
+  // Text-verification shortcut (see csfm_common.cuh): only when no interval is asked for (a
+  // verified query yields its count, 0 or 1, but not its final SA row) and the batch bytes are
+  // 16-byte aligned (the pattern window is staged with 16-byte cp.async copies).
+  __shared__ VerifySlot vslots[kThreads / 4];
+  VerifySlot& vs = vslots[threadIdx.x >> 2];
+  const bool shortcut = iv.text != nullptr && a.sp_ep == nullptr && a.row_sp == nullptr &&
+                        (reinterpret_cast<uintptr_t>(a.bytes) & 15) == 0;
+  const uint8_t* const batch_end = shortcut ? a.bytes + a.offs[a.npat] : nullptr;
+  const uint32_t dense_mask = (1u << iv.dense_shift) - 1u;
+
   bool active = false;
   unsigned long long q = 0;      // query index
   const uint8_t* ptr = nullptr;  // address of the character being processed
   uint32_t rem = 0;              // characters left including the current one
   uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
-  uint32_t my_steps = 0, my_lookups = 0;
+  uint32_t vstage = 0, vp = 0;   // 0 searching, 1 suffix-array entry requested, 2 windows in flight
+  uint32_t my_steps = 0, my_lookups = 0, my_checks = 0;
 
   auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
     if (j == 0) {
@@ -160,21 +171,70 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
+    // ---- text verification of one-row intervals, two trips behind the step that found them ----
+    if (__any_sync(0xFFFFFFFFu, vstage != 0)) {  // warp-uniform
+      if (vstage == 2) cp_async_wait_all();       // the copies this lane issued last trip
+      __syncwarp();                               // ... and those of its three neighbours
+      bool same = true;
+      if (vstage == 2) {
+        // text[vp-rem .. vp) against pattern[ptr-rem .. ptr): 8 characters per lane
+        const uint32_t toff = (vp - rem) & 15u;
+        const uint32_t poff = (uint32_t)(reinterpret_cast<uintptr_t>(ptr - rem) & 15u);
+#pragma unroll
+        for (uint32_t i = 0; i < kVerifyMax / 4; ++i) {
+          const uint32_t k = (kVerifyMax / 4) * j + i;
+          if (k < rem) same = same && (vs.t[toff + k] == vs.p[poff + k]);
+        }
+      }
+      const unsigned votes = __ballot_sync(0xFFFFFFFFu, same);
+      if (vstage == 2) {
+        const bool all4 = ((votes >> (lane & ~3)) & 0xFu) == 0xFu;
+        vstage = 0;
+        finish(all4 ? 1u : 0u, 0, 0);  // the row stays a single row while the characters match
+      } else if (vstage == 1) {
+        const uint8_t* pstart = ptr - rem;
+        const uintptr_t pal = reinterpret_cast<uintptr_t>(pstart) & ~(uintptr_t)15;
+        const uint32_t np16 = (uint32_t)((reinterpret_cast<uintptr_t>(ptr) - pal + 15) >> 4);
+        if (vp < rem || reinterpret_cast<const uint8_t*>(pal) + 16 * np16 > batch_end) {
+          // the occurrence would wrap around the text start (cyclic BWT), or the aligned pattern
+          // window would leave the batch: go on stepping
+          vstage = 0;
+          --ptr;
+          begin_step(next_byte);
+        } else {
+          const uint32_t tstart = vp - rem, tal = tstart & ~15u;
+          const uint32_t nt16 = (vp - tal + 15) >> 4;
+          if ((uint32_t)j < nt16) cp_async16(&vs.t[16 * j], iv.text + tal + 16 * j);
+          if ((uint32_t)j < np16) cp_async16(&vs.p[16 * j], reinterpret_cast<const uint8_t*>(pal) + 16 * j);
+          cp_async_commit();
+          vstage = 2;
+        }
+      }
+    }
+
     // ---- one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
+    const bool ranking = active && vstage == 0;
     uint32_t rs, re;
     if (two) {
-      rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re);
+      rank_pair(lv0, code >> 4, sp, ep, ranking, j, rs, re);
       sp = add0 + rs;
       ep = add0 + re;
     }
-    rank_pair(lv_last, code & 15u, sp, ep, active, j, rs, re);
-    if (active) {
+    rank_pair(lv_last, code & 15u, sp, ep, ranking, j, rs, re);
+    if (ranking) {
       sp = base + rs;  // fm_index.cpp:92-93
       ep = base + re;
       if (sp >= ep) {
         finish(0, 0, 0);
       } else if (--rem == 0) {
         finish(ep - sp, sp, ep);
+      } else if (shortcut && ep - sp == 1 && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+        // One row left: its suffix starts at SA[sp]; the query matches iff the rem characters
+        // before that text position equal the rest of the pattern. Ask for SA[sp] now, use it
+        // next trip.
+        vp = iv.dense[sp >> iv.dense_shift];
+        vstage = 1;
+        ++my_checks;
       } else {
         --ptr;
         begin_step(next_byte);
@@ -182,13 +242,15 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
   }
   if (a.steps_total) {
-    unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0;
+    unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0, u = (j == 0) ? my_checks : 0;
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
       t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+      u += __shfl_xor_sync(0xFFFFFFFFu, u, o);
     }
     if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
     if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
+    if (lane == 0 && u) atomicAdd(a.steps_total + 2, (unsigned long long)u);
   }
 }
 

@@ -72,6 +72,10 @@ typedef struct {
 #define CSFM_BUILD_LAYOUT_BINARY64 4u /* layout 1: binary wavelet matrix in 64-byte lines (one bit
                                          per line fetch) instead of the default layout 2: 16-ary
                                          levels in 128-byte lines (four bits per line fetch) */
+#define CSFM_BUILD_NO_TEXT_CHECK 16u /* do not keep the text + suffix array for the verification
+                                        shortcut (kept by default when the text ends in a unique
+                                        smallest byte: a query whose interval has shrunk to one row
+                                        then compares its remaining characters with the text) */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
 
@@ -89,6 +93,8 @@ typedef struct {
   uint32_t layout;     /* 1 = binary / 64-byte lines, 2 = 16-ary / 128-byte lines */
   uint32_t line_bytes; /* bytes fetched per rank per level: 64 or 128 */
   uint32_t kmer_k;     /* length of the k-mer jump table's keys, 0 = no table */
+  uint32_t text_check; /* 1 = text + suffix array resident for the verification shortcut */
+  uint32_t reserved;
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */
@@ -101,6 +107,9 @@ typedef struct {
   float kernel_ms;          /* device time of the dominant kernel (CUDA events), 0 unless asked */
   uint32_t table_lookups;   /* queries that started from the k-mer table (their first k steps are
                                not in search_steps); 0 unless asked */
+  uint32_t text_checks;     /* queries finished by comparing their remaining characters with the
+                               text (those characters are not in search_steps); 0 unless asked */
+  uint32_t reserved;
 } csfm_call_stats;
 
 CSFM_API const char* csfm_last_error(void);

@@ -354,3 +354,54 @@ def test_async_submit_wait(fm):
         oc, ose = orc.count_batch(d, o)
         assert (hc.numpy().astype(np.uint64) == oc).all()
         assert (hs.numpy().astype(np.uint64).reshape(-1, 2) == ose).all()
+
+
+@pytest.mark.parametrize("sigma,n", [(4, 300_000), (255, 400_000), (20, 50_000)])
+def test_text_verification_shortcut(fm, sigma, n):
+    """Counts WITHOUT intervals take the shortcut: once a query's interval is a single row, its
+    remaining characters are compared with the text. Same counts as the oracle and as an index
+    built without the text sections, for hits, near misses, cyclic wrap-arounds, patterns with the
+    terminator inside, long patterns and bytes outside the alphabet."""
+    rng = np.random.default_rng(sigma * 7 + n)
+    alpha = np.sort(rng.choice(np.arange(1, 256), sigma, replace=False)).astype(np.uint8)
+    text = np.concatenate([alpha[rng.integers(0, sigma, n - 1)], np.zeros(1, np.uint8)]).astype(np.uint8)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32))
+    assert idx.info().text_check == 1
+    plain = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32), flags=fm.BUILD_NO_TEXT_CHECK)
+    assert plain.info().text_check == 0
+    orc = oracle.OracleIndex(text, stride=32)
+    pats = []
+    for _ in range(6000):
+        m = int(rng.integers(1, 41))
+        s = int(rng.integers(0, n - m))
+        p = text[s:s + m].copy()
+        r = rng.random()
+        if r < 0.35 and m > 1:
+            p[int(rng.integers(0, m))] = alpha[rng.integers(0, sigma)]      # near miss anywhere
+        elif r < 0.45:
+            p[0] = 0xFF                                                    # byte outside the alphabet, at the far end
+        pats.append(p.tobytes())
+    for k in (1, 2, 5, 17, 31, 40):                                        # cyclic: ... end of text, terminator, start of text
+        for t in (1, 3, 9, 30):
+            pats.append(np.concatenate([text[n - k:], text[:t]]).tobytes())
+    pats += [text[s:s + m].tobytes() for s, m in zip(rng.integers(0, n - 3000, 30), rng.integers(60, 2500, 30))]
+    pats += [text[:m].tobytes() for m in (1, 2, 8, 33, 70)] + [b"", text[-1:].tobytes()]
+    d, o = fm.pack_patterns(pats)
+    oc, _ = orc.count_batch(d, o)
+    idx.set_instrumentation(1)
+    got = idx.count_batch(d, o)
+    st = idx.last_call_stats()
+    assert (got == oc).all()
+    assert st.text_checks > 1000                       # the shortcut really ran
+    assert (plain.count_batch(d, o) == oc).all()
+    # with intervals requested the shortcut is off and the intervals are exact
+    c2, se2 = idx.count_batch(d, o, want_intervals=True)
+    oc2, ose2 = orc.count_batch(d, o)
+    assert (c2 == oc2).all() and (se2 == ose2).all()
+
+
+def test_no_text_check_without_a_unique_smallest_terminator(fm):
+    for text in (b"banana", b"abab$abab$", b"zzz\x01zzz\x00\x00"):
+        idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=2))
+        assert idx.info().text_check == 0
+    assert fm.FMIndex.build_from_text(b"banana$", fm.BuildParams(ssa_stride=2)).info().text_check == 1
