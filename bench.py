@@ -393,12 +393,13 @@ def run_engine(args, rank, world, local_rank):
 
     # exact executed-step counts per batch (S of the roofline model) + correctness properties
     idx.set_instrumentation(1)
-    steps_per_batch, lookups_per_batch = [], []
+    steps_per_batch, lookups_per_batch, checks_per_batch = [], [], []
     for b in range(NB):
         step_device(b)
         stream.synchronize()
         steps_per_batch.append(int(idx.last_call_stats().search_steps))
         lookups_per_batch.append(int(idx.last_call_stats().table_lookups))
+        checks_per_batch.append(int(idx.last_call_stats().text_checks))
         if b == 0:
             c0 = d_counts.cpu().numpy().copy()
             assert (c0 >= 1).all(), "text-sampled patterns must occur at least once"
@@ -481,8 +482,10 @@ def run_engine(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (count_kernel) ------------------------------------------------
     peak, peak_src = measured_peak()
     line_bytes = int(info.line_bytes)
-    # executed traffic model: every rank step reads 2 x L lines, every k-mer table lookup one line
-    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + lookups_per_batch[i % NB] * 128 for i in range(args.steps)]
+    # executed traffic model: every rank step reads 2 x L lines, every k-mer table lookup one line,
+    # every text verification two (the suffix-array entry and the text window)
+    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + lookups_per_batch[i % NB] * 128 + checks_per_batch[i % NB] * 256
+                 for i in range(args.steps)]
     achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
@@ -498,12 +501,14 @@ def run_engine(args, rank, world, local_rank):
                 "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
                 "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
                 "table_lookups_per_launch": float(np.mean([lookups_per_batch[i % NB] for i in range(args.steps)])),
-                "kmer_k": int(info.kmer_k),
+                "text_checks_per_launch": float(np.mean([checks_per_batch[i % NB] for i in range(args.steps)])),
+                "kmer_k": int(info.kmer_k), "text_check": int(info.text_check),
                 "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
                 "note": "duration per launch = CUDA events on the launching stream around each step "
-                        "(32-byte cursor memset + the count kernel). achieved = algorithmic bytes (rank steps x 2 x L x "
-                        "line + table lookups x 128 B) / duration; sp and ep share a line after ~4 steps, so the real "
-                        "DRAM traffic (`traffic`, ncu) is about half of that and frac can exceed 1"}
+                        "(32-byte cursor memset + the count kernel). achieved = executed algorithmic bytes (rank steps x 2 "
+                        "x L x line + table lookups x 128 B + text verifications x 256 B) / duration; sp and ep often "
+                        "share a line, so the real DRAM traffic (`traffic`, ncu) is lower. The binding ceiling is the "
+                        "random 128-byte fetch RATE (frac_of_random_fetch_ceiling), not streaming bandwidth"}
     if traffic:
         # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)
         roofline["dram_gbs_from_traffic"] = traffic / (total_ms / args.steps / 1e3) / 1e9

@@ -402,7 +402,11 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // is unique and the smallest present (then row r <-> suffix SA[r] and LF(r) <-> SA[r]-1 cyclically,
   // so "keep stepping from a one-row interval" equals "compare with the text"; without such a
   // terminator the reference's BWT is not a rotation BWT and the shortcut would change results).
-  if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK)) {
+  // Worth it only when the levels live in HBM: stepping through L2-resident lines is cheaper than
+  // the two HBM fetches (suffix-array entry, text) of a verification.
+  const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
+  if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
+      (levels_in_hbm || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
     uint8_t last = 0;
     cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
     if (e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0) {

@@ -111,6 +111,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // in one go; the two windows (text, pattern) are staged in a per-sub-warp slot as aligned 16-byte
 // chunks (a window of 32 unaligned bytes spans at most three of them).
 constexpr uint32_t kVerifyMax = 32;
+constexpr uint32_t kVerifyMin = 3;  // fewer characters left: stepping costs no more than verifying
 struct alignas(16) VerifySlot {
   uint8_t t[48];
   uint8_t p[48];
@@ -155,7 +156,7 @@ struct WalkArgs {
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging);
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
-int max_blocks_per_sm_count2(bool tma_staging);
+int max_blocks_per_sm_count2(bool tma_staging, const IndexView& iv, const CountArgs& a);
 int max_blocks_per_sm_walk2();
 int max_blocks_per_sm_access2();
 

@@ -342,7 +342,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   a.steps_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
   const bool tma = idx->tma_staging;
-  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2(tma) : persistent_grid(idx, (const void*)count_kernel);
+  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2(tma, idx->view, a) : persistent_grid(idx, (const void*)count_kernel);
   const uint64_t want = (npat * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;

@@ -53,7 +53,10 @@ __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32
 // ------------------------------------------------------------------------------------------
 // Default variant: pattern offsets and bytes are read straight from global memory (two dependent
 // loads when a sub-warp starts a pattern, then a one-step byte prefetch).
-__global__ void __launch_bounds__(kThreads, 8)
+// kShortcut: compiled with the text-verification stages (used when the index carries the text, no
+// interval is asked for and the batch is 16-byte aligned); the plain variant keeps 32 registers.
+template <bool kShortcut>
+__global__ void __launch_bounds__(kThreads, kShortcut ? 6 : 8)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
   load_tables(tb, iv.hdr);
@@ -69,10 +72,9 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   // Text-verification shortcut (see csfm_common.cuh): only when no interval is asked for (a
   // verified query yields its count, 0 or 1, but not its final SA row) and the batch bytes are
   // 16-byte aligned (the pattern window is staged with 16-byte cp.async copies).
-  __shared__ VerifySlot vslots[kThreads / 4];
-  VerifySlot& vs = vslots[threadIdx.x >> 2];
-  const bool shortcut = iv.text != nullptr && a.sp_ep == nullptr && a.row_sp == nullptr &&
-                        (reinterpret_cast<uintptr_t>(a.bytes) & 15) == 0;
+  __shared__ VerifySlot vslots[kShortcut ? kThreads / 4 : 1];
+  VerifySlot& vs = vslots[kShortcut ? (threadIdx.x >> 2) : 0];
+  constexpr bool shortcut = kShortcut;
   const uint8_t* const batch_end = shortcut ? a.bytes + a.offs[a.npat] : nullptr;
   const uint32_t dense_mask = (1u << iv.dense_shift) - 1u;
 
@@ -172,7 +174,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
     // ---- text verification of one-row intervals, two trips behind the step that found them ----
-    if (__any_sync(0xFFFFFFFFu, vstage != 0)) {  // warp-uniform
+    if (kShortcut && __any_sync(0xFFFFFFFFu, vstage != 0)) {  // warp-uniform
       if (vstage == 2) cp_async_wait_all();       // the copies this lane issued last trip
       __syncwarp();                               // ... and those of its three neighbours
       bool same = true;
@@ -228,7 +230,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         finish(0, 0, 0);
       } else if (--rem == 0) {
         finish(ep - sp, sp, ep);
-      } else if (shortcut && ep - sp == 1 && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+      } else if (shortcut && ep - sp == 1 && rem >= kVerifyMin && rem <= kVerifyMax && (sp & dense_mask) == 0) {
         // One row left: its suffix starts at SA[sp]; the query matches iff the rem characters
         // before that text position equal the rest of the pattern. Ask for SA[sp] now, use it
         // next trip.
@@ -665,11 +667,19 @@ int blocks_per_sm(const void* kernel) {
 
 }  // namespace
 
+// The verification variant needs the text sections, no interval outputs and 16-byte aligned bytes.
+static bool use_shortcut(const IndexView& iv, const CountArgs& a) {
+  return iv.text != nullptr && a.sp_ep == nullptr && a.row_sp == nullptr &&
+         (reinterpret_cast<uintptr_t>(a.bytes) & 15) == 0;
+}
+
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging) {
   if (tma_staging)
     count2_tma_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+  else if (use_shortcut(iv, a))
+    count2_kernel<true><<<grid, kThreads, 0, stream>>>(iv, a);
   else
-    count2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+    count2_kernel<false><<<grid, kThreads, 0, stream>>>(iv, a);
 }
 int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
   const BlobHeader& h = idx->h;
@@ -694,8 +704,9 @@ void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
   access2_kernel<<<grid, kThreads, 0, stream>>>(iv, out);
 }
-int max_blocks_per_sm_count2(bool tma_staging) {
-  return blocks_per_sm(tma_staging ? (const void*)count2_tma_kernel : (const void*)count2_kernel);
+int max_blocks_per_sm_count2(bool tma_staging, const IndexView& iv, const CountArgs& a) {
+  if (tma_staging) return blocks_per_sm((const void*)count2_tma_kernel);
+  return use_shortcut(iv, a) ? blocks_per_sm((const void*)count2_kernel<true>) : blocks_per_sm((const void*)count2_kernel<false>);
 }
 int max_blocks_per_sm_walk2() { return blocks_per_sm((const void*)walk2_kernel); }
 int max_blocks_per_sm_access2() { return blocks_per_sm((const void*)access2_kernel); }

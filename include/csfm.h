@@ -76,6 +76,10 @@ typedef struct {
                                         shortcut (kept by default when the text ends in a unique
                                         smallest byte: a query whose interval has shrunk to one row
                                         then compares its remaining characters with the text) */
+#define CSFM_BUILD_FORCE_TEXT_CHECK 32u /* keep them even when the levels are small enough to live in
+                                           L2 (by default the shortcut is built only for indexes whose
+                                           levels exceed 96 MB: below that, stepping through L2-resident
+                                           lines is faster than two HBM fetches) */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
 

@@ -50,7 +50,7 @@ def _check_queries(fm, idx, case):
 
 
 @pytest.mark.parametrize("case", FM["cases"], ids=[c["name"] for c in FM["cases"]])
-@pytest.mark.parametrize("flags", [0, 1, 4, 5], ids=["nib128", "nib128-rawbytes", "bin64", "bin64-8levels"])
+@pytest.mark.parametrize("flags", [0, 1, 4, 5, 32], ids=["nib128", "nib128-rawbytes", "bin64", "bin64-8levels", "nib128-textcheck"])
 def test_golden_from_text(fm, case, flags):
     """build_from_text on the GPU (SA -> BWT -> C -> wavelet -> SSA) + queries vs the reference."""
     text = bytes.fromhex(case["text_hex"])
@@ -58,7 +58,7 @@ def test_golden_from_text(fm, case, flags):
     info = idx.info()
     assert info.n == case["n"]
     assert info.layout == (1 if flags & 4 else 2) and info.line_bytes == (64 if flags & 4 else 128)
-    assert info.levels == {0: info.levels, 1: 2, 4: info.levels, 5: 8}[flags] and 1 <= info.levels <= 8
+    assert info.levels == {0: info.levels, 1: 2, 4: info.levels, 5: 8, 32: info.levels}[flags] and 1 <= info.levels <= 8
     assert idx.C_array().tolist() == case["C"]
     assert idx.ssa().tolist() == case["ssa"]
     assert idx.bwt().tobytes() == bytes.fromhex(case["bwt_hex"])
@@ -365,8 +365,9 @@ def test_text_verification_shortcut(fm, sigma, n):
     rng = np.random.default_rng(sigma * 7 + n)
     alpha = np.sort(rng.choice(np.arange(1, 256), sigma, replace=False)).astype(np.uint8)
     text = np.concatenate([alpha[rng.integers(0, sigma, n - 1)], np.zeros(1, np.uint8)]).astype(np.uint8)
-    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32))
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32), flags=fm.BUILD_FORCE_TEXT_CHECK)
     assert idx.info().text_check == 1
+    assert fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32)).info().text_check == 0  # small: levels fit in L2
     plain = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32), flags=fm.BUILD_NO_TEXT_CHECK)
     assert plain.info().text_check == 0
     orc = oracle.OracleIndex(text, stride=32)
@@ -402,6 +403,6 @@ def test_text_verification_shortcut(fm, sigma, n):
 
 def test_no_text_check_without_a_unique_smallest_terminator(fm):
     for text in (b"banana", b"abab$abab$", b"zzz\x01zzz\x00\x00"):
-        idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=2))
+        idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=2), flags=fm.BUILD_FORCE_TEXT_CHECK)
         assert idx.info().text_check == 0
-    assert fm.FMIndex.build_from_text(b"banana$", fm.BuildParams(ssa_stride=2)).info().text_check == 1
+    assert fm.FMIndex.build_from_text(b"banana$", fm.BuildParams(ssa_stride=2), flags=fm.BUILD_FORCE_TEXT_CHECK).info().text_check == 1
