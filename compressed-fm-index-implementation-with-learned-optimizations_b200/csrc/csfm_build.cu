@@ -329,6 +329,10 @@ int index_finish_handle(csfm_index* idx) {
   v.text = h.off_text ? idx->d_blob + h.off_text : nullptr;
   v.dense = h.off_text ? reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_dense) : nullptr;
   v.dense_shift = h.dense_shift;
+  // a verification costs two HBM fetches and three loop trips; a step costs `levels` fetches and
+  // one trip: worth it from 3 characters left on a two-level index, from 8 on a one-level index
+  v.verify_min = h.levels >= 2 ? 3u : 8u;
+  if (const char* e = std::getenv("CSFM_VERIFY_MIN")) v.verify_min = (uint32_t)std::atoi(e);
   if (std::getenv("CSFM_NO_TEXT_CHECK")) v.text = nullptr;  // experiment knob: ignore the sections
   if (std::getenv("CSFM_NO_KMER_TABLE")) {  // experiment knob: ignore a table that is present
     v.kmer = nullptr;
@@ -404,9 +408,12 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // terminator the reference's BWT is not a rotation BWT and the shortcut would change results).
   // Worth it only when the levels live in HBM: stepping through L2-resident lines is cheaper than
   // the two HBM fetches (suffix-array entry, text) of a verification.
+  // On a one-level index (sigma <= 16) a step is a single fetch and the plain kernel (32 registers,
+  // full occupancy) wins unless patterns are long: measured on the 4e9-byte DNA text, 2.68e9 q/s
+  // plain vs 2.37e9 with the verification variant that never fires. So: two levels, in HBM.
   const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
   if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
-      (levels_in_hbm || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
+      ((levels_in_hbm && L == 2) || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
     uint8_t last = 0;
     cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
     if (e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0) {

@@ -112,7 +112,7 @@ struct IndexView {
   uint32_t layout;
   uint32_t stride_shift;  // log2(stride) when the stride is a power of two, else 32
   uint32_t dense_shift;
-  uint32_t pad1;
+  uint32_t verify_min;  // verify against the text only when at least this many characters are left
   uint32_t zeros[kMaxLevels];
 };
 

@@ -111,7 +111,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // in one go; the two windows (text, pattern) are staged in a per-sub-warp slot as aligned 16-byte
 // chunks (a window of 32 unaligned bytes spans at most three of them).
 constexpr uint32_t kVerifyMax = 32;
-constexpr uint32_t kVerifyMin = 3;  // fewer characters left: stepping costs no more than verifying
 struct alignas(16) VerifySlot {
   uint8_t t[48];
   uint8_t p[48];

@@ -230,7 +230,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         finish(0, 0, 0);
       } else if (--rem == 0) {
         finish(ep - sp, sp, ep);
-      } else if (shortcut && ep - sp == 1 && rem >= kVerifyMin && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+      } else if (shortcut && ep - sp == 1 && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
         // One row left: its suffix starts at SA[sp]; the query matches iff the rem characters
         // before that text position equal the rest of the pattern. Ask for SA[sp] now, use it
         // next trip.

@@ -76,10 +76,11 @@ typedef struct {
                                         shortcut (kept by default when the text ends in a unique
                                         smallest byte: a query whose interval has shrunk to one row
                                         then compares its remaining characters with the text) */
-#define CSFM_BUILD_FORCE_TEXT_CHECK 32u /* keep them even when the levels are small enough to live in
-                                           L2 (by default the shortcut is built only for indexes whose
-                                           levels exceed 96 MB: below that, stepping through L2-resident
-                                           lines is faster than two HBM fetches) */
+#define CSFM_BUILD_FORCE_TEXT_CHECK 32u /* keep them for every text with such a terminator. By default the
+                                           shortcut is built only for two-level indexes (more than 16
+                                           distinct bytes) whose levels exceed 96 MB: below that, stepping
+                                           through L2-resident lines, or through one-fetch steps, is faster
+                                           than the two HBM fetches of a verification */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
 
