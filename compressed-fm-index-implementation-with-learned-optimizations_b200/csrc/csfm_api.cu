@@ -395,13 +395,13 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   cudaStream_t st = idx->stream;
   // input staging: [offs (npat+1) u64][bytes]
   const size_t offs_bytes = (npat + 1) * 8;
-  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 16);
+  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 512);
   if (rc) return rc;
   const size_t out_bytes = npat * 8 * (sp_ep ? 3 : 1);
   rc = idx->ws_out.ensure(out_bytes);
   if (rc) return rc;
   uint64_t* d_offs = idx->ws_in.as<uint64_t>();
-  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + offs_bytes;
+  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + ((offs_bytes + 255) & ~(size_t)255);  // aligned: TMA / cp.async staging
   uint64_t* d_counts = idx->ws_out.as<uint64_t>();
   uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
   idx->stats.h2d_bytes = offs_bytes + nbytes;
@@ -458,12 +458,12 @@ int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_
   *ticket = t;
   if (npat == 0) return CSFM_OK;
   const size_t offs_bytes = (npat + 1) * 8;
-  int rc = sl.in.ensure(offs_bytes + nbytes + 16);
+  int rc = sl.in.ensure(offs_bytes + nbytes + 512);
   if (rc) return rc;
   rc = sl.out.ensure(npat * 8 * (sp_ep ? 3 : 1));
   if (rc) return rc;
   uint64_t* d_offs = sl.in.as<uint64_t>();
-  uint8_t* d_bytes = sl.in.as<uint8_t>() + offs_bytes;
+  uint8_t* d_bytes = sl.in.as<uint8_t>() + ((offs_bytes + 255) & ~(size_t)255);  // aligned: TMA / cp.async staging
   uint64_t* d_counts = sl.out.as<uint64_t>();
   uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
   CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, sl.stream));
@@ -529,12 +529,12 @@ int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* off
   const size_t offs_bytes = (npat + 1) * 8;
   const size_t status_bytes = (npat * 4 + 7) / 8 * 8;
   // ws_in: [offs][bytes] ; ws_out: [out_offs (npat+1) u64][status npat i32] ; ws_pos: positions
-  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 16);
+  int rc = idx->ws_in.ensure(offs_bytes + nbytes + 512);
   if (rc) return rc;
   rc = idx->ws_out.ensure(offs_bytes + status_bytes);
   if (rc) return rc;
   uint64_t* d_offs = idx->ws_in.as<uint64_t>();
-  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + offs_bytes;
+  uint8_t* d_bytes = idx->ws_in.as<uint8_t>() + ((offs_bytes + 255) & ~(size_t)255);  // aligned: TMA / cp.async staging
   uint64_t* d_out_offs = idx->ws_out.as<uint64_t>();
   int32_t* d_status = reinterpret_cast<int32_t*>(idx->ws_out.as<uint8_t>() + offs_bytes);
   CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, st));
