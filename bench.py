@@ -425,6 +425,41 @@ def run_engine(args, rank, world, local_rank):
     step_ms = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)])
     launches = args.steps * 1  # one count_kernel per step (the 32-byte cursor memset is not a kernel)
 
+    # ---- the stepping-only kernel on the same index (count2_kernel<false>): asking for the [sp,ep)
+    # intervals rules the text verification out, so every query runs the plain backward search
+    stepping = None
+    if int(info.text_check) and int(info.layout) == 2:
+        d_spep = torch.zeros(2 * batch, dtype=torch.int64, device=dev)
+
+        def step_plain(b):
+            bytes_d, offs_d = d_batches[b % NB]
+            idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), batch, d_counts.data_ptr(), d_spep.data_ptr(),
+                                   stream.cuda_stream)
+
+        idx.set_instrumentation(1)
+        step_plain(0)
+        stream.synchronize()
+        plain_steps = int(idx.last_call_stats().search_steps)
+        plain_lookups = int(idx.last_call_stats().table_lookups)
+        idx.set_instrumentation(0)
+        plain_equal = bool((d_counts.cpu().numpy() == c0).all())
+        K2 = min(args.steps, 40)
+        for i in range(3):
+            step_plain(i)
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K2):
+            step_plain(i)
+        e1.record(stream)
+        stream.synchronize()
+        plain_ms = e0.elapsed_time(e1) / K2
+        stepping = {"kernel": "count2_kernel<false>", "ms_per_launch": plain_ms, "launches_timed": K2,
+                    "queries_per_s": batch / (plain_ms / 1e3), "search_steps_per_launch": plain_steps,
+                    "table_lookups_per_launch": plain_lookups, "counts_equal_default_kernel": plain_equal}
+        launches += K2 + 4
+        del d_spep
+
     # ---- timed region 2: end to end through the host-pointer C ABI ------------------------------------
     # The streaming form of the public API (csfm_count_batch_submit / _wait): every step copies its
     # own patterns + offsets host->device from pinned memory and its own counts device->host, all
@@ -497,7 +532,8 @@ def run_engine(args, rank, world, local_rank):
             traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kernel_name = ("count2_tma_kernel" if os.environ.get("CSFM_PATTERN_STAGING") == "tma" else "count2_kernel") \
+    kernel_name = ("count2_tma_kernel" if os.environ.get("CSFM_PATTERN_STAGING") == "tma" else
+                   ("count2_kernel<true>" if int(info.text_check) else "count2_kernel<false>")) \
         if int(info.layout) == 2 else "count_kernel"
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -519,6 +555,21 @@ def run_engine(args, rank, world, local_rank):
                                    "gbs": ref_steps * 2 * L * line_bytes / (total_ms / args.steps / 1e3) / 1e9,
                                    "note": "what the reference's step-by-step search would move for the same batch; the "
                                            "engine skips most of it (k-mer table, shared lines, text verification)"}
+    if stepping:
+        pb = stepping["search_steps_per_launch"] * 2 * L * line_bytes + stepping["table_lookups_per_launch"] * 128
+        stepping["algorithmic_bytes_per_launch"] = pb
+        stepping["achieved_gbs"] = pb / (stepping["ms_per_launch"] / 1e3) / 1e9
+        stepping["frac"] = stepping["achieved_gbs"] / peak
+        try:
+            t2 = json.load(open(tp)).get(args.workload + "_no_text_check", {}).get("dram_bytes_per_launch")
+        except Exception:
+            t2 = None
+        if t2:
+            stepping["traffic"] = t2
+            stepping["frac_of_random_fetch_ceiling"] = t2 / 128 / (stepping["ms_per_launch"] / 1e3) / 37.3e9
+        stepping["note"] = ("the same batches through the plain backward-search kernel (every character a rank step; "
+                            "selected by asking for the intervals), for comparison with the default kernel above")
+        roofline["stepping_only"] = stepping
     if traffic:
         # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)
         roofline["dram_gbs_from_traffic"] = traffic / (total_ms / args.steps / 1e3) / 1e9
@@ -565,7 +616,7 @@ def run_engine(args, rank, world, local_rank):
         "config": {"workload": wl["desc"], "n": n, "levels": L, "line_bytes": int(info.line_bytes), "layout": int(info.layout),
                    "sigma": int(info.sigma), "batch_per_gpu": batch,
                    "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
-                   "l2_policy": "inputs larger than L2: 1.15 GB index + a different 28 MB batch every step" if n >= (1 << 29)
+                   "l2_policy": f"inputs larger than L2: {info.blob_bytes / 1e9:.2f} GB index + a different 28 MB batch every step" if n >= (1 << 29)
                    else "index is L2-resident at this size; a different batch every step",
                    "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"])},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -333,6 +333,10 @@ int index_finish_handle(csfm_index* idx) {
   // one trip: worth it from 3 characters left on a two-level index, from 8 on a one-level index
   v.verify_min = h.levels >= 2 ? 3u : 8u;
   if (const char* e = std::getenv("CSFM_VERIFY_MIN")) v.verify_min = (uint32_t)std::atoi(e);
+  v.refill_min = 8;
+  v.refill_wait = 5;
+  if (const char* e = std::getenv("CSFM_REFILL_MIN")) v.refill_min = (uint32_t)std::min(8, std::max(1, std::atoi(e)));
+  if (const char* e = std::getenv("CSFM_REFILL_WAIT")) v.refill_wait = (uint32_t)std::max(1, std::atoi(e));
   if (std::getenv("CSFM_NO_TEXT_CHECK")) v.text = nullptr;  // experiment knob: ignore the sections
   if (std::getenv("CSFM_NO_KMER_TABLE")) {  // experiment knob: ignore a table that is present
     v.kmer = nullptr;

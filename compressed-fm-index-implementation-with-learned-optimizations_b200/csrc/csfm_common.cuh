@@ -113,6 +113,8 @@ struct IndexView {
   uint32_t stride_shift;  // log2(stride) when the stride is a power of two, else 32
   uint32_t dense_shift;
   uint32_t verify_min;  // verify against the text only when at least this many characters are left
+  uint32_t refill_min;   // shortcut kernel: a warp fetches new queries once this many of its sub-warps are idle ...
+  uint32_t refill_wait;  // ... or this many trips after its last refill, whichever comes first
   uint32_t zeros[kMaxLevels];
 };
 

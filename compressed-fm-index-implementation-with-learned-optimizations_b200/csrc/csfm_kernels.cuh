@@ -38,11 +38,15 @@ struct WarpQueue {
 
 // Called by all 32 lanes (converged). `need` = this sub-warp wants an item. Returns the item
 // index or ~0ull. A partially served round simply leaves some sub-warps idle for one trip.
+// min_idle > 1 batches the refills of a warp: nothing is handed out until that many sub-warps are
+// idle, so the refill code (issued for the whole warp whoever needs it) runs on fewer trips.
+// `served` (warp-uniform) tells whether anything was handed out.
 __device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need, int lane,
                                                          unsigned long long* cursor,
-                                                         unsigned long long total) {
+                                                         unsigned long long total, unsigned min_idle, bool& served) {
+  served = false;
   const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & 0x11111111u;  // leaders
-  if (need_mask == 0) return ~0ull;
+  if ((unsigned)__popc(need_mask) < min_idle) return ~0ull;
   if (q.next >= q.end && !q.exhausted) {
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
@@ -60,7 +64,13 @@ __device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need
   unsigned long long item = ~0ull;
   if (need && my_rank < avail) item = q.next + my_rank;
   q.next += (cnt < avail) ? cnt : avail;
+  served = avail != 0;
   return item;
+}
+__device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need, int lane,
+                                                         unsigned long long* cursor, unsigned long long total) {
+  bool served;
+  return queue_take(q, need, lane, cursor, total, 1u, served);
 }
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX): pattern staging ------------------------
