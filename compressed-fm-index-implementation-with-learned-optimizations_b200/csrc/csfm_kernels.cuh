@@ -117,14 +117,39 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Text-verification shortcut: at most kVerifyMax remaining characters are compared with the text
-// in one go; the two windows (text, pattern) are staged in a per-sub-warp slot as aligned 16-byte
-// chunks (a window of 32 unaligned bytes spans at most three of them).
+// Text-verification shortcut: once the interval of a query is down to at most kVerifyRows rows
+// and at most kVerifyMax characters are left, lane j of the sub-warp compares those characters
+// with the text in front of the suffix of row sp + j. The windows (one text window per row, one
+// pattern window) are staged in a per-sub-warp slot as aligned 16-byte chunks: a window of 32
+// unaligned bytes spans at most three of them.
 constexpr uint32_t kVerifyMax = 32;
+constexpr uint32_t kVerifyRows = 4;
 struct alignas(16) VerifySlot {
-  uint8_t t[48];
+  uint8_t t[kVerifyRows][48];
   uint8_t p[48];
+  uint8_t pad[16];
 };
+
+// t[toff + k] == p[poff + k] for all k < rem (rem <= kVerifyMax, toff and poff < 16), four
+// characters at a time: both windows are re-aligned with funnel shifts, the bytes past rem masked.
+__device__ __forceinline__ bool windows_equal(const uint8_t* t, const uint8_t* p, uint32_t toff, uint32_t poff,
+                                              uint32_t rem) {
+  const uint32_t* tw = reinterpret_cast<const uint32_t*>(t) + (toff >> 2);
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(p) + (poff >> 2);
+  const uint32_t ts = (toff & 3u) * 8u, ps = (poff & 3u) * 8u;
+  uint32_t acc = 0, tlo = tw[0], plo = pw[0];
+#pragma unroll
+  for (uint32_t w = 0; w < kVerifyMax / 4; ++w) {
+    const uint32_t thi = tw[w + 1], phi = pw[w + 1];
+    const uint32_t x = __funnelshift_r(tlo, thi, ts) ^ __funnelshift_r(plo, phi, ps);
+    const int left = (int)rem - (int)(4 * w);                 // characters from this word on
+    const uint32_t valid = (uint32_t)min(max(left, 0), 4);    // ... that belong to this word
+    acc |= x & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * valid);
+    tlo = thi;
+    plo = phi;
+  }
+  return acc == 0;
+}
 
 constexpr uint32_t kStageBytes = 2048;  // pattern bytes staged per warp chunk (32 patterns)
 constexpr uint32_t kPrivBytes = 64;     // private slot per sub-warp for the pattern it is working on

@@ -77,6 +77,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   constexpr bool shortcut = kShortcut;
   const uint8_t* const batch_end = shortcut ? a.bytes + a.offs[a.npat] : nullptr;
   const uint32_t dense_mask = (1u << iv.dense_shift) - 1u;
+  const uint32_t max_rows = iv.dense_shift == 0 ? kVerifyRows : 1u;  // neighbouring rows need the full suffix array
 
   bool active = false;
   unsigned long long q = 0;      // query index
@@ -185,43 +186,49 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
-    // ---- text verification of one-row intervals, two trips behind the step that found them ----
+    // ---- text verification of narrow intervals, two trips behind the step that found them ----
+    // sp and ep stay as that step left them while vstage != 0: lane j owns row sp + j.
     if (kShortcut && __any_sync(0xFFFFFFFFu, vstage != 0)) {  // warp-uniform
-      if (vstage == 2) cp_async_wait_all();       // the copies this lane issued last trip
-      __syncwarp();                               // ... and those of its three neighbours
-      bool same = true;
-      if (vstage == 2) {
-        // text[vp-rem .. vp) against pattern[ptr-rem .. ptr): 8 characters per lane
-        const uint32_t toff = (vp - rem) & 15u;
-        const uint32_t poff = (uint32_t)(reinterpret_cast<uintptr_t>(ptr - rem) & 15u);
-#pragma unroll
-        for (uint32_t i = 0; i < kVerifyMax / 4; ++i) {
-          const uint32_t k = (kVerifyMax / 4) * j + i;
-          if (k < rem) same = same && (vs.t[toff + k] == vs.p[poff + k]);
+      const uint32_t rows = ep - sp;
+      if (__any_sync(0xFFFFFFFFu, vstage == 2)) {
+        if (vstage == 2) cp_async_wait_all();  // the copies this lane issued last trip
+        __syncwarp();                          // ... and those of its three neighbours
+        bool hit = false;
+        if (vstage == 2 && (uint32_t)j < rows)
+          hit = windows_equal(vs.t[j], vs.p, (vp - rem) & 15u, (uint32_t)(reinterpret_cast<uintptr_t>(ptr - rem) & 15u), rem);
+        const unsigned votes = __ballot_sync(0xFFFFFFFFu, hit);
+        if (vstage == 2) {
+          // a row stays in the interval exactly while the characters in front of its suffix match
+          vstage = 0;
+          finish(__popc((votes >> (lane & ~3)) & 0xFu), 0, 0);
         }
       }
-      const unsigned votes = __ballot_sync(0xFFFFFFFFu, same);
-      if (vstage == 2) {
-        const bool all4 = ((votes >> (lane & ~3)) & 0xFu) == 0xFu;
-        vstage = 0;
-        finish(all4 ? 1u : 0u, 0, 0);  // the row stays a single row while the characters match
-      } else if (vstage == 1) {
+      if (__any_sync(0xFFFFFFFFu, vstage == 1)) {
         const uint8_t* pstart = ptr - rem;
         const uintptr_t pal = reinterpret_cast<uintptr_t>(pstart) & ~(uintptr_t)15;
         const uint32_t np16 = (uint32_t)((reinterpret_cast<uintptr_t>(ptr) - pal + 15) >> 4);
-        if (vp < rem || reinterpret_cast<const uint8_t*>(pal) + 16 * np16 > batch_end) {
-          // the occurrence would wrap around the text start (cyclic BWT), or the aligned pattern
-          // window would leave the batch: go on stepping
-          vstage = 0;
-          --ptr;
-          begin_step(next_byte);
-        } else {
-          const uint32_t tstart = vp - rem, tal = tstart & ~15u;
-          const uint32_t nt16 = (vp - tal + 15) >> 4;
-          if ((uint32_t)j < nt16) cp_async16(&vs.t[16 * j], iv.text + tal + 16 * j);
-          if ((uint32_t)j < np16) cp_async16(&vs.p[16 * j], reinterpret_cast<const uint8_t*>(pal) + 16 * j);
-          cp_async_commit();
-          vstage = 2;
+        // an occurrence that would wrap around the text start (cyclic BWT), or an aligned pattern
+        // window that would leave the batch: that query goes on stepping
+        const bool bad = vstage == 1 && (((uint32_t)j < rows && vp < rem) ||
+                                         reinterpret_cast<const uint8_t*>(pal) + 16 * np16 > batch_end);
+        const unsigned bads = __ballot_sync(0xFFFFFFFFu, bad);
+        if (vstage == 1) {
+          if ((bads >> (lane & ~3)) & 0xFu) {
+            vstage = 0;
+            --ptr;
+            begin_step(next_byte);
+          } else {
+            if ((uint32_t)j < rows) {
+              const uint32_t tal = (vp - rem) & ~15u;
+              const uint32_t nt16 = (vp - tal + 15) >> 4;
+#pragma unroll
+              for (uint32_t c = 0; c < 3; ++c)
+                if (c < nt16) cp_async16(&vs.t[j][16 * c], iv.text + tal + 16 * c);
+            }
+            if ((uint32_t)j < np16) cp_async16(&vs.p[16 * j], reinterpret_cast<const uint8_t*>(pal) + 16 * j);
+            cp_async_commit();
+            vstage = 2;
+          }
         }
       }
     }
@@ -229,13 +236,13 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // ---- one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
     const bool ranking = active && vstage == 0;
     if (kShortcut && !__any_sync(0xFFFFFFFFu, ranking)) continue;  // a trip of verifications only
-    uint32_t rs, re;
+    uint32_t rs, re, s1 = sp, e1 = ep;  // sp and ep themselves must survive a trip spent in verification
     if (two) {
       rank_pair(lv0, code >> 4, sp, ep, ranking, j, rs, re);
-      sp = add0 + rs;
-      ep = add0 + re;
+      s1 = add0 + rs;
+      e1 = add0 + re;
     }
-    rank_pair(lv_last, code & 15u, sp, ep, ranking, j, rs, re);
+    rank_pair(lv_last, code & 15u, s1, e1, ranking, j, rs, re);
     if (ranking) {
       sp = base + rs;  // fm_index.cpp:92-93
       ep = base + re;
@@ -243,11 +250,11 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         finish(0, 0, 0);
       } else if (--rem == 0) {
         finish(ep - sp, sp, ep);
-      } else if (shortcut && ep - sp == 1 && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
-        // One row left: its suffix starts at SA[sp]; the query matches iff the rem characters
-        // before that text position equal the rest of the pattern. Ask for SA[sp] now, use it
-        // next trip.
-        vp = iv.dense[sp >> iv.dense_shift];
+      } else if (shortcut && ep - sp <= max_rows && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+        // Few rows left: the suffix of row r starts at SA[r], and r stays in the interval iff the
+        // rem characters before that text position equal the rest of the pattern. Ask for the
+        // suffix-array entries now (lane j: row sp + j), use them next trip.
+        if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
         vstage = 1;
         ++my_checks;
       } else {
