@@ -467,26 +467,44 @@ def run_engine(args, rank, world, local_rank):
     # overlap the kernel of another.
     DEPTH = 3
     h_out = [torch.zeros(batch, dtype=torch.int64).pin_memory() for _ in range(DEPTH)]
+    # compact form (csfm_count_batch_submit32): u32 offsets in, u32 counts out
+    h_offs32 = []
+    for hb, ho in h_batches:
+        assert int(ho[-1]) < 2 ** 32
+        o32 = torch.empty(ho.numel(), dtype=torch.int32).pin_memory()
+        o32.copy_(ho.to(torch.int32))  # values < 2^31 here; the C side reads them as unsigned
+        h_offs32.append(o32)
+    h_out32 = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, compact):
         tickets = []
         for i in range(nsteps):
             hb, ho = h_batches[i % NB]
             if i >= DEPTH:
                 idx.count_batch_wait(tickets[i - DEPTH])  # frees output buffer i % DEPTH
-            tickets.append(idx.count_batch_submit(hb.data_ptr(), ho.data_ptr(), batch, h_out[i % DEPTH].data_ptr()))
+            if compact:
+                tickets.append(idx.count_batch_submit32(hb.data_ptr(), h_offs32[i % NB].data_ptr(), batch, h_out32[i % DEPTH].data_ptr()))
+            else:
+                tickets.append(idx.count_batch_submit(hb.data_ptr(), ho.data_ptr(), batch, h_out[i % DEPTH].data_ptr()))
         for t in tickets[-DEPTH:]:
             idx.count_batch_wait(t)
 
-    e2e_run(max(3, args.warmup))
-    torch.cuda.synchronize()
-    barrier()
     e2e_steps = args.steps
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    e2e_times = {}
+    for compact in (False, True):
+        e2e_run(max(3, args.warmup), compact)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps, compact)
+        torch.cuda.synchronize()
+        e2e_times[compact] = time.perf_counter() - t0
+        barrier()
+        if compact:
+            st32 = idx.last_call_stats()
+            h2d32, d2h32 = int(st32.h2d_bytes), int(st32.d2h_bytes)
+    e2e_s, e2e_s_u64 = e2e_times[True], e2e_times[False]
+    compact_equal = bool((h_out32[(e2e_steps - 1) % DEPTH].numpy().astype(np.int64) == h_out[(e2e_steps - 1) % DEPTH].numpy()).all())
     h_counts = h_out[(e2e_steps - 1) % DEPTH]
     # the synchronous call (csfm_count_batch) for comparison: one step at a time, nothing overlapped
     h_sync = torch.zeros(batch, dtype=torch.int64).pin_memory()
@@ -501,16 +519,17 @@ def run_engine(args, rank, world, local_rank):
             raise RuntimeError(L_.csfm_last_error().decode())
     e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / min(20, e2e_steps)
     st = idx.last_call_stats()
-    h2d, d2h = int(st.h2d_bytes), int(st.d2h_bytes)
+    h2d64, d2h64 = int(st.h2d_bytes), int(st.d2h_bytes)
+    h2d, d2h = h2d32, d2h32
     step_device(e2e_steps - 1)  # same batch as the last end-to-end step: both paths must agree
     stream.synchronize()
     e2e_equal = bool((h_counts.numpy() == d_counts.cpu().numpy()).all())
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_s_u64], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
+        total_ms, e2e_s, e2e_s_u64 = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         return
 
@@ -621,13 +640,17 @@ def run_engine(args, rank, world, local_rank):
                    "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"])},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": "csfm_count_batch_submit/_wait (host pointers, pinned, 3 steps in flight)",
+                "api": "csfm_count_batch_submit32/_wait (host pointers, pinned, u32 offsets and counts, 3 steps in flight)",
+                "kernels_per_step": 3,
+                "u64_api": {"value": world * e2e_steps * batch / e2e_s_u64, "ms_per_step": 1e3 * e2e_s_u64 / e2e_steps,
+                            "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
+                            "api": "csfm_count_batch_submit/_wait (u64 offsets and counts)"},
                 "sync_call_ms_per_step": e2e_sync_ms, "sync_call_value": world * batch / (e2e_sync_ms / 1e3)},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clocks.summary(),
-        "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal},
+        "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal, "compact_equals_u64_api": compact_equal},
         "locate": locate,
     }
     emit(line)

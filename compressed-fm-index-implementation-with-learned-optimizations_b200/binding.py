@@ -79,6 +79,7 @@ SIGNATURES = {
     "csfm_count_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp]),
     "csfm_count_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
     "csfm_count_batch_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "csfm_count_batch_submit32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_wait": (C.c_int, [_vp, C.c_uint64]),
     "csfm_locate_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_locate_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp,
@@ -318,6 +319,12 @@ class FMIndex:
         t = C.c_uint64()
         _check(lib().csfm_count_batch_submit(self._h, _vp(bytes_ptr), _vp(offs_ptr), npat, _vp(counts_ptr),
                                              _vp(sp_ep_ptr) if sp_ep_ptr else None, C.byref(t)))
+        return int(t.value)
+
+    def count_batch_submit32(self, bytes_ptr: int, offs32_ptr: int, npat: int, counts32_ptr: int) -> int:
+        """Compact asynchronous count: u32 offsets in, u32 counts out (less PCIe traffic per query)."""
+        t = C.c_uint64()
+        _check(lib().csfm_count_batch_submit32(self._h, _vp(bytes_ptr), _vp(offs32_ptr), npat, _vp(counts32_ptr), C.byref(t)))
         return int(t.value)
 
     def count_batch_wait(self, ticket: int):

@@ -3,6 +3,7 @@
 // Host logic only: argument checks, host<->device staging for the host-pointer entry points,
 // workspace reuse, accounting. No algorithm lives here and nothing here can run a query on the
 // CPU: every path ends in a kernel launch from csfm_query.cu / csfm_build.cu / csfm_sa.cu.
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -477,6 +478,62 @@ int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_
   if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, sl.stream));
   idx->stats.h2d_bytes = offs_bytes + nbytes;
   idx->stats.d2h_bytes = npat * 8 * (sp_ep ? 3 : 1);
+  return CSFM_OK;
+}
+
+namespace {
+__global__ void widen_offsets_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t count) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+__global__ void narrow_counts_kernel(const uint64_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t count) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = (uint32_t)in[i];
+}
+}  // namespace
+
+int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint32_t* offs32, uint64_t npat,
+                              uint32_t* counts32, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!offs32 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
+  const uint64_t nbytes = npat ? offs32[npat] : 0;
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const uint64_t t = idx->next_ticket++;
+  csfm_index::AsyncSlot& sl = idx->async_slot[t % CSFM_ASYNC_SLOTS];
+  if (!sl.stream) CSFM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  if (sl.ticket) CSFM_CUDA(cudaStreamSynchronize(sl.stream));  // slot still busy with an older batch
+  sl.ticket = t;
+  *ticket = t;
+  if (npat == 0) return CSFM_OK;
+  // input slot: [offs (npat+1) u64][bytes, 256-byte aligned][offs32 as copied, 256-byte aligned]
+  const size_t offs_bytes = (npat + 1) * 8;
+  const size_t bytes_at = (offs_bytes + 255) & ~(size_t)255;
+  const size_t offs32_at = (bytes_at + nbytes + 255) & ~(size_t)255;
+  int rc = sl.in.ensure(offs32_at + (npat + 1) * 4 + 512);
+  if (rc) return rc;
+  rc = sl.out.ensure(npat * 8 + npat * 4);  // [counts u64][counts u32]
+  if (rc) return rc;
+  uint64_t* d_offs = sl.in.as<uint64_t>();
+  uint8_t* d_bytes = sl.in.as<uint8_t>() + bytes_at;
+  uint32_t* d_offs32 = reinterpret_cast<uint32_t*>(sl.in.as<uint8_t>() + offs32_at);
+  uint64_t* d_counts = sl.out.as<uint64_t>();
+  uint32_t* d_counts32 = reinterpret_cast<uint32_t*>(d_counts + npat);
+  CSFM_CUDA(cudaMemcpyAsync(d_offs32, offs32, (npat + 1) * 4, cudaMemcpyHostToDevice, sl.stream));
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  const int grid = (int)std::min<uint64_t>((npat + 1 + 255) / 256, (uint64_t)idx->num_sms * 8);
+  widen_offsets_kernel<<<grid, 256, 0, sl.stream>>>(d_offs32, d_offs, npat + 1);
+  CSFM_CUDA(cudaGetLastError());
+  const uint32_t saved = idx->instr_mask;
+  idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
+  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, nullptr, nullptr, nullptr, 0, sl.stream);
+  idx->instr_mask = saved;
+  if (rc) return rc;
+  narrow_counts_kernel<<<grid, 256, 0, sl.stream>>>(d_counts, d_counts32, npat);
+  CSFM_CUDA(cudaGetLastError());
+  CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
+  idx->stats.h2d_bytes = (npat + 1) * 4 + nbytes;
+  idx->stats.d2h_bytes = npat * 4;
   return CSFM_OK;
 }
 

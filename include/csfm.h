@@ -175,6 +175,11 @@ CSFM_API int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint6
 CSFM_API int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs,
                                      uint64_t npat, uint64_t* counts, uint64_t* sp_ep,
                                      uint64_t* ticket);
+/* Compact form of submit for PCIe-bound streams: 32-bit offsets (offs32[npat] < 2^32) and 32-bit
+ * counts (a count never exceeds n < 2^32). Same tickets, same slots, waited on with
+ * csfm_count_batch_wait; the offsets are widened and the counts narrowed on the device. */
+CSFM_API int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint32_t* offs32,
+                                       uint64_t npat, uint32_t* counts32, uint64_t* ticket);
 CSFM_API int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket);
 CSFM_API int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes,
                                      const uint64_t* d_offs, uint64_t npat, uint64_t* d_counts,

@@ -356,6 +356,37 @@ def test_async_submit_wait(fm):
         assert (hs.numpy().astype(np.uint64).reshape(-1, 2) == ose).all()
 
 
+@pytest.mark.parametrize("force_text", [False, True])
+def test_async_submit32_compact(fm, force_text):
+    """csfm_count_batch_submit32: u32 offsets in, u32 counts out, mixed with the u64 form on the same slots."""
+    import torch
+    rng = np.random.default_rng(77)
+    text, alpha = _rand_text(rng, 150_000, 90, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16), flags=fm.BUILD_FORCE_TEXT_CHECK if force_text else 0)
+    orc = oracle.OracleIndex(text, stride=16)
+    jobs = []
+    for k in range(8):
+        pats = _mixed_patterns(rng, text, alpha, 3000 + 101 * k, 24) if k != 5 else [b""]
+        d, o = fm.pack_patterns(pats)
+        hb = torch.from_numpy(d.copy()).pin_memory() if d.size else torch.zeros(1, dtype=torch.uint8).pin_memory()
+        npat = o.size - 1
+        if k % 3 == 2:
+            ho = torch.from_numpy(o.astype(np.int64)).pin_memory()
+            hc = torch.zeros(npat, dtype=torch.int64).pin_memory()
+            t = idx.count_batch_submit(hb.data_ptr(), ho.data_ptr(), npat, hc.data_ptr())
+        else:
+            ho = torch.from_numpy(o.astype(np.uint32).view(np.int32)).pin_memory()
+            hc = torch.full((npat,), -1, dtype=torch.int32).pin_memory()
+            t = idx.count_batch_submit32(hb.data_ptr(), ho.data_ptr(), npat, hc.data_ptr())
+        jobs.append((t, d, o, hb, ho, hc))
+    for t, d, o, hb, ho, hc in jobs:
+        idx.count_batch_wait(t)
+        oc, _ = orc.count_batch(d, o)
+        got = hc.numpy()
+        got = got.view(np.uint32) if got.dtype == np.int32 else got
+        assert (got.astype(np.uint64) == oc).all()
+
+
 @pytest.mark.parametrize("sigma,n", [(4, 300_000), (255, 400_000), (20, 50_000)])
 def test_text_verification_shortcut(fm, sigma, n):
     """Counts WITHOUT intervals take the shortcut: once a query's interval is a single row, its
@@ -399,6 +430,42 @@ def test_text_verification_shortcut(fm, sigma, n):
     c2, se2 = idx.count_batch(d, o, want_intervals=True)
     oc2, ose2 = orc.count_batch(d, o)
     assert (c2 == oc2).all() and (se2 == ose2).all()
+
+
+@pytest.mark.parametrize("copies,sigma", [(2, 200), (3, 60), (4, 30), (7, 120)])
+def test_text_verification_of_several_rows(fm, copies, sigma):
+    """Near-repeats: the text is `copies` mutated copies of one block, so most patterns narrow to 2..copies
+    rows that the remaining characters then tell apart (up to four rows are verified lane by lane,
+    more keep stepping). Counts 0..copies all occur."""
+    rng = np.random.default_rng(copies * 1000 + sigma)
+    block = rng.integers(1, sigma + 1, 20_000).astype(np.uint8)
+    parts = []
+    for _ in range(copies):
+        b = block.copy()
+        hit = rng.random(b.size) < 0.02
+        b[hit] = rng.integers(1, sigma + 1, int(hit.sum())).astype(np.uint8)
+        parts.append(b)
+    text = np.concatenate(parts + [np.zeros(1, np.uint8)]).astype(np.uint8)
+    n = text.size
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16), flags=fm.BUILD_FORCE_TEXT_CHECK)
+    assert idx.info().text_check == 1
+    orc = oracle.OracleIndex(text, stride=16)
+    pats = []
+    for _ in range(8000):
+        m = int(rng.integers(4, 45))
+        s = int(rng.integers(0, n - m))
+        p = text[s:s + m].copy()
+        if rng.random() < 0.2:
+            p[int(rng.integers(0, m))] = rng.integers(1, sigma + 1)
+        pats.append(p.tobytes())
+    d, o = fm.pack_patterns(pats)
+    oc, _ = orc.count_batch(d, o)
+    idx.set_instrumentation(1)
+    got = idx.count_batch(d, o)
+    assert (got == oc).all()
+    assert idx.last_call_stats().text_checks > 1000
+    seen = set(np.unique(oc).tolist())
+    assert set(range(0, min(copies, 4) + 1)) <= seen
 
 
 def test_no_text_check_without_a_unique_smallest_terminator(fm):
