@@ -454,7 +454,7 @@ def run_engine(args, rank, world, local_rank):
         e1.record(stream)
         stream.synchronize()
         plain_ms = e0.elapsed_time(e1) / K2
-        stepping = {"kernel": "count2_kernel<false>", "ms_per_launch": plain_ms, "launches_timed": K2,
+        stepping = {"kernel": "count2_kernel<false,false>", "ms_per_launch": plain_ms, "launches_timed": K2,
                     "queries_per_s": batch / (plain_ms / 1e3), "search_steps_per_launch": plain_steps,
                     "table_lookups_per_launch": plain_lookups, "counts_equal_default_kernel": plain_equal}
         launches += K2 + 4
@@ -552,7 +552,7 @@ def run_engine(args, rank, world, local_rank):
         except Exception:
             traffic = None
     kernel_name = ("count2_tma_kernel" if os.environ.get("CSFM_PATTERN_STAGING") == "tma" else
-                   ("count2_kernel<true>" if int(info.text_check) else "count2_kernel<false>")) \
+                   ("count2_kernel<true,false>" if int(info.text_check) else "count2_kernel<false,false>")) \
         if int(info.layout) == 2 else "count_kernel"
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

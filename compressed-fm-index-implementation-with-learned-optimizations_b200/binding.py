@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcsfm.so")
+LIB_PATH = os.environ.get("CSFM_LIB") or os.path.join(HERE, "libcsfm.so")  # CSFM_LIB: an experiment build of the same sources
 
 CSFM_OK, CSFM_ERR_INVALID, CSFM_ERR_CUDA, CSFM_ERR_NOMEM, CSFM_ERR_TOO_LARGE, CSFM_ERR_CAPACITY, CSFM_ERR_FORMAT = range(7)
 Q_OK, Q_LF_WALK_EXCEEDED, Q_SSA_OOB = 0, 1, 2

@@ -3,7 +3,7 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-OUT="$HERE/libcsfm.so"
+OUT="${CSFM_OUT:-$HERE/libcsfm.so}"  # CSFM_OUT / CSFM_NVCC_EXTRA: experiment builds beside the product library
 SRCS=("$HERE"/csrc/csfm_api.cu "$HERE"/csrc/csfm_build.cu "$HERE"/csrc/csfm_query.cu "$HERE"/csrc/csfm_query2.cu "$HERE"/csrc/csfm_sa.cu)
 newest=$(ls -t "$HERE"/csrc/* "$HERE"/../include/csfm.h "$HERE"/build.sh | head -1)
 if [[ -f "$OUT" && "$OUT" -nt "$newest" && "${1:-}" != "-f" ]]; then
@@ -11,5 +11,5 @@ if [[ -f "$OUT" && "$OUT" -nt "$newest" && "${1:-}" != "-f" ]]; then
 fi
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
   -Xcompiler -fPIC,-fvisibility=hidden,-Wall -Xptxas -v \
-  --shared -o "$OUT" "${SRCS[@]}" -ccbin /usr/bin/g++ 2> "$HERE/build.log" || { cat "$HERE/build.log" >&2; exit 1; }
+  ${CSFM_NVCC_EXTRA:-} --shared -o "$OUT" "${SRCS[@]}" -ccbin /usr/bin/g++ 2> "$HERE/build.log" || { cat "$HERE/build.log" >&2; exit 1; }
 grep -E "error|warning: v|registers|spill" "$HERE/build.log" | grep -v "^$" | head -60 || true

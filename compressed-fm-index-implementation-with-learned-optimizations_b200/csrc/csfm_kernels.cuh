@@ -73,6 +73,38 @@ __device__ __forceinline__ unsigned long long queue_take(WarpQueue& q, bool need
   return queue_take(q, need, lane, cursor, total, 1u, served);
 }
 
+// 32-bit form for kernels whose launches stay below 2^32 items (count_device slices at 2^31):
+// two registers less per thread. Returns the item index or ~0u.
+struct WarpQueue32 {
+  uint32_t next = 0, end = 0;
+  bool exhausted = false;
+};
+__device__ __forceinline__ uint32_t queue_take32(WarpQueue32& q, bool need, int lane, unsigned long long* cursor,
+                                                 uint32_t total, unsigned min_idle, bool& served) {
+  served = false;
+  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & 0x11111111u;  // leaders
+  if ((unsigned)__popc(need_mask) < min_idle) return ~0u;
+  if (q.next >= q.end && !q.exhausted) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) {
+      q.exhausted = true;
+    } else {
+      q.next = (uint32_t)base;
+      q.end = (total - q.next > kChunk) ? q.next + kChunk : total;
+    }
+  }
+  const uint32_t avail = q.end - q.next;
+  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
+  const unsigned cnt = __popc(need_mask);
+  uint32_t item = ~0u;
+  if (need && my_rank < avail) item = q.next + my_rank;
+  q.next += (cnt < avail) ? cnt : avail;
+  served = avail != 0;
+  return item;
+}
+
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX): pattern staging ------------------------
 // cp.async.bulk moves a contiguous, 16-byte aligned span global -> shared through the TMA unit
 // (SASS: UBLKCP) and signals an mbarrier with the byte count; nobody spends registers or issue

@@ -55,8 +55,12 @@ __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32
 // loads when a sub-warp starts a pattern, then a one-step byte prefetch).
 // kShortcut: compiled with the text-verification stages (used when the index carries the text, no
 // interval is asked for and the batch is 16-byte aligned); the plain variant keeps 32 registers.
-template <bool kShortcut>
-__global__ void __launch_bounds__(kThreads, kShortcut ? 6 : 8)  // measured: 6 beats 5 (no spills) and 8 (more spills)
+#ifndef CSFM_SHORTCUT_CTAS
+#define CSFM_SHORTCUT_CTAS 6  // measured: 6 beats 5 (no spills) and 8 (more spills)
+#endif
+// kInstr: compiled with the per-call step / lookup / verification counters (csfm_set_instrumentation).
+template <bool kShortcut, bool kInstr>
+__global__ void __launch_bounds__(kThreads, kShortcut ? CSFM_SHORTCUT_CTAS : 8)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
   load_tables(tb, iv.hdr);
@@ -67,7 +71,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const uint8_t* const lv0 = iv.levels + j * 32;
   const uint8_t* const lv_last = iv.levels_last + j * 32;
   const uint32_t kk = iv.kmer_k;  // 0 = no jump table
-  WarpQueue wq;
+  WarpQueue32 wq;
 
   // Text-verification shortcut (see csfm_common.cuh): only when no interval is asked for (a
   // verified query yields its count, 0 or 1, but not its final SA row) and the batch bytes are
@@ -80,7 +84,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const uint32_t max_rows = iv.dense_shift == 0 ? kVerifyRows : 1u;  // neighbouring rows need the full suffix array
 
   bool active = false;
-  unsigned long long q = 0;      // query index
+  uint32_t q = 0;                // query index (a launch stays below 2^32 queries)
   const uint8_t* ptr = nullptr;  // address of the character being processed
   uint32_t rem = 0;              // characters left including the current one
   uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
@@ -92,8 +96,8 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (j == 0) {
       if (a.counts) a.counts[q] = cnt;
       if (a.sp_ep) {
-        a.sp_ep[2 * q] = lo;
-        a.sp_ep[2 * q + 1] = hi;
+        a.sp_ep[2 * (uint64_t)q] = lo;
+        a.sp_ep[2 * (uint64_t)q + 1] = hi;
       }
       if (a.row_sp) {
         a.row_sp[q] = lo;
@@ -104,7 +108,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   };
   // Sets up the step that prepends byte b to the interval [sp,ep).
   auto begin_step = [&](uint32_t b) {
-    ++my_steps;
+    if (kInstr) ++my_steps;
     if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
       finish(0, 0, 0);
       return;
@@ -121,24 +125,20 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // stages together (refill+step, suffix-array entry, windows, compare), so a trip runs only
     // the sections its generation is in. A generation is not held up for more than refill_wait
     // trips by a query that keeps stepping.
-    unsigned long long item;
-    if (kShortcut) {
-      bool served;
-      item = queue_take(wq, !active, lane, a.cursor, a.npat, since_refill >= iv.refill_wait ? 1u : iv.refill_min, served);
-      since_refill = served ? 0u : since_refill + 1u;
-    } else {
-      item = queue_take(wq, !active, lane, a.cursor, a.npat);
-    }
-    if (item != ~0ull) {
+    bool served;
+    const uint32_t item = queue_take32(wq, !active, lane, a.cursor, (uint32_t)a.npat,
+                                       kShortcut && since_refill < iv.refill_wait ? iv.refill_min : 1u, served);
+    if (kShortcut) since_refill = served ? 0u : since_refill + 1u;
+    if (item != ~0u) {
       q = item;
-      const uint64_t o0 = a.offs[q], o1 = a.offs[q + 1];
+      const uint64_t o0 = a.offs[q], o1 = a.offs[(uint64_t)q + 1];
       const uint64_t m = o1 - o0;
       active = true;
       if (m == 0) {
         // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
         if (j == 0) {
           if (a.counts) a.counts[q] = iv.n;
-          if (a.sp_ep) { a.sp_ep[2 * q] = 0; a.sp_ep[2 * q + 1] = 0; }
+          if (a.sp_ep) { a.sp_ep[2 * (uint64_t)q] = 0; a.sp_ep[2 * (uint64_t)q + 1] = 0; }
           if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
         }
         active = false;
@@ -153,7 +153,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           e += tb.code_of_byte[b] * mul;
           mul *= iv.kmer_radix;
         }
-        ++my_lookups;
+        if (kInstr) ++my_lookups;
         uint2 se = make_uint2(0, 0);
         if (present) se = iv.kmer[e];
         sp = se.x;
@@ -172,7 +172,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         const uint32_t b = a.bytes[o1 - 1];
         sp = tb.C[b];
         ep = tb.C[b + 1];
-        ++my_steps;
+        if (kInstr) ++my_steps;
         if (sp >= ep) {
           finish(0, 0, 0);
         } else if (m == 1) {
@@ -256,14 +256,14 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         // suffix-array entries now (lane j: row sp + j), use them next trip.
         if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
         vstage = 1;
-        ++my_checks;
+        if (kInstr) ++my_checks;
       } else {
         --ptr;
         begin_step(next_byte);
       }
     }
   }
-  if (a.steps_total) {
+  if (kInstr && a.steps_total) {
     unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0, u = (j == 0) ? my_checks : 0;
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
@@ -696,10 +696,13 @@ static bool use_shortcut(const IndexView& iv, const CountArgs& a) {
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging) {
   if (tma_staging)
     count2_tma_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
-  else if (use_shortcut(iv, a))
-    count2_kernel<true><<<grid, kThreads, 0, stream>>>(iv, a);
-  else
-    count2_kernel<false><<<grid, kThreads, 0, stream>>>(iv, a);
+  else if (use_shortcut(iv, a)) {
+    if (a.steps_total) count2_kernel<true, true><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count2_kernel<true, false><<<grid, kThreads, 0, stream>>>(iv, a);
+  } else {
+    if (a.steps_total) count2_kernel<false, true><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count2_kernel<false, false><<<grid, kThreads, 0, stream>>>(iv, a);
+  }
 }
 int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
   const BlobHeader& h = idx->h;
@@ -726,7 +729,8 @@ void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t st
 }
 int max_blocks_per_sm_count2(bool tma_staging, const IndexView& iv, const CountArgs& a) {
   if (tma_staging) return blocks_per_sm((const void*)count2_tma_kernel);
-  return use_shortcut(iv, a) ? blocks_per_sm((const void*)count2_kernel<true>) : blocks_per_sm((const void*)count2_kernel<false>);
+  return use_shortcut(iv, a) ? blocks_per_sm((const void*)count2_kernel<true, false>)
+                             : blocks_per_sm((const void*)count2_kernel<false, false>);
 }
 int max_blocks_per_sm_walk2() { return blocks_per_sm((const void*)walk2_kernel); }
 int max_blocks_per_sm_access2() { return blocks_per_sm((const void*)access2_kernel); }
