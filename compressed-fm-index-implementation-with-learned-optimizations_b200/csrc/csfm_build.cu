@@ -389,10 +389,12 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
   h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
   // k-mer jump table: the first k steps of a query become one lookup. Budget: a quarter of the
-  // level bytes, between 1 MiB and 128 MiB (k = 3 for a byte alphabet at n = 2^30, 9 for DNA+$ at 2^26).
+  // level bytes, between 1 MiB and 1 GiB (k = 3 for a byte alphabet at n = 2^30, 9 for DNA+$ at 2^26,
+  // 11 for DNA+$ at 4e9).
   if (nib && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
     const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : h.sigma;
-    const uint64_t budget = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
+    uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
+    if (const char* e = std::getenv("CSFM_KMER_BUDGET_MB")) budget = (uint64_t)std::max(1, std::atoi(e)) << 20;
     uint32_t k = 0;
     uint64_t entries = 1;
     while (radix >= 2 && entries * radix * 8 <= budget && k < 16) {
@@ -416,6 +418,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // full occupancy) wins unless patterns are long: measured on the 4e9-byte DNA text, 2.68e9 q/s
   // plain vs 2.37e9 with the verification variant that never fires. So: two levels, in HBM.
   const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
+  if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
   if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
       ((levels_in_hbm && L == 2) || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
     uint8_t last = 0;
