@@ -282,7 +282,7 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
   BlobHeader h;
   CSFM_CUDA(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost));
-  if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 2) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
+  if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 3) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
   const bool nib = h.layout == kLayoutNibble128;
   const uint64_t per_line = nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
   if ((h.layout != kLayoutNibble128 && h.layout != kLayoutBinary64) || h.total_bytes > bytes || h.levels == 0 ||

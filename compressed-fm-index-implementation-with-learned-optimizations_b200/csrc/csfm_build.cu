@@ -155,12 +155,10 @@ nib_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, int shift, uint8_t*
       // histogram: one shared add per distinct value per round
       const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? v : 0xFFu);
       if (valid && lane == __ffs(peers) - 1) hist[wib][v] += __popc(peers);
-      // round r = chunk r; symbol s = lane of the chunk goes to word s&3, nibble s>>2
-      uint32_t x = v << (4 * (lane >> 2));
-      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 4);
-      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 8);
-      x |= __shfl_xor_sync(0xFFFFFFFFu, x, 16);
-      if (lane < 4) line[line_word_of_payload(4 * r + lane)] = x;
+      // round r = chunk r, lane = symbol of the chunk; payload word b = bit b of the 32 symbols
+      const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, v & 1u), b1 = __ballot_sync(0xFFFFFFFFu, v & 2u);
+      const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, v & 4u), b3 = __ballot_sync(0xFFFFFFFFu, v & 8u);
+      if (lane < 4) line[line_word_of_payload(4 * r + lane)] = lane == 0 ? b0 : lane == 1 ? b1 : lane == 2 ? b2 : b3;
       __syncwarp();
     }
     if (lane < 16) linecnt[(uint64_t)lane * nblk + b] = hist[wib][lane];
@@ -375,7 +373,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   BlobHeader& h = idx->h;
   std::memset(&h, 0, sizeof h);
   std::memcpy(h.magic, "CSFMDEV1", 8);
-  h.version = 2;
+  h.version = 3;  // 3: bit-sliced chunk payload
   h.n = n;
   h.stride = stride;
   h.nsamp = nsamp;

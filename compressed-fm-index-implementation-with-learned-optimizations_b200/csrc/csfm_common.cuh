@@ -168,17 +168,19 @@ __device__ __forceinline__ uint32_t lane_partial_rank(uint4 w, uint32_t off, int
   return r;
 }
 
-// layout 2: symbol s (0..31) of a chunk lives in payload word s&3, nibble s>>2 (interleaved), so
-// that the four per-word match masks fold into ONE 32-bit hit word in symbol order:
-// bit s of chunk_hits() is set <=> symbol s of the chunk equals the nibble replicated in `pat`.
-__device__ __forceinline__ uint32_t nibble_eq_msb(uint32_t w, uint32_t pat) {
-  const uint32_t x = w ^ pat;                              // zero nibble <=> match
-  const uint32_t t = (x & 0x77777777u) + 0x77777777u;      // bit 3 set <=> low 3 bits != 0
-  return ~(t | x) & 0x88888888u;                           // bit 3 of every matching nibble
+// layout 2: the 32 symbols of a chunk are stored BIT-SLICED: payload word b holds bit b of every
+// symbol (bit s of word b = bit b of symbol s). "Which symbols equal v" is then four logic
+// operations on whole words and comes out in symbol order:
+// bit s of chunk_hits() is set <=> symbol s of the chunk equals v (0..15).
+__device__ __forceinline__ uint32_t bit_fill(uint32_t v, int b) {  // all ones if bit b of v is set, else 0
+  return 0u - ((v >> b) & 1u);
 }
-__device__ __forceinline__ uint32_t chunk_hits(const Chunk32& k, uint32_t pat) {
-  return (nibble_eq_msb(k.p0, pat) >> 3) | (nibble_eq_msb(k.p1, pat) >> 2) | (nibble_eq_msb(k.p2, pat) >> 1) |
-         nibble_eq_msb(k.p3, pat);
+__device__ __forceinline__ uint32_t chunk_hits(const Chunk32& k, uint32_t v) {
+  uint32_t miss = k.p0 ^ bit_fill(v, 0);
+  miss |= k.p1 ^ bit_fill(v, 1);
+  miss |= k.p2 ^ bit_fill(v, 2);
+  miss |= k.p3 ^ bit_fill(v, 3);
+  return ~miss;
 }
 // Branch-free pick of one of four registers by a 2-bit index (selp chain: the ternary form
 // compiles to divergent branches).
@@ -211,8 +213,7 @@ __device__ __forceinline__ uint32_t chunk_partial(uint32_t cnt, uint32_t hits, u
 // the symbol at offset off of a line, given this lane's chunk (valid in lane off>>5 only)
 __device__ __forceinline__ uint32_t chunk_symbol(const Chunk32& k, uint32_t off) {
   const uint32_t s = off & 31u;
-  const uint32_t w = pick4(k.p0, k.p1, k.p2, k.p3, s);
-  return (w >> (4u * (s >> 2))) & 15u;
+  return ((k.p0 >> s) & 1u) | (((k.p1 >> s) & 1u) << 1) | (((k.p2 >> s) & 1u) << 2) | (((k.p3 >> s) & 1u) << 3);
 }
 
 // SA rows are sampled at multiples of the stride (fm_index.cpp:57-65): no hardware divide for the

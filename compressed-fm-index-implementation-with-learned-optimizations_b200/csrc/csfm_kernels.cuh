@@ -30,6 +30,17 @@ __device__ __forceinline__ void load_tables(Tables& t, const BlobHeader* __restr
   __syncthreads();
 }
 
+// Everything a backward-search step needs to know about its byte, in one 16-byte shared load:
+// x = base_by_byte, y = compact code (bit 31 set: byte absent from the text), z = start1[code >> 4].
+// Call before load_tables() (which ends with the CTA barrier).
+__device__ __forceinline__ void load_step_table(uint4* step, const BlobHeader* __restrict__ h) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint32_t code = h->code_of_byte[i];
+    const bool absent = h->C[i + 1] == h->C[i];
+    step[i] = make_uint4(h->base_by_byte[i], code | (absent ? 0x80000000u : 0u), h->start1[code >> 4], 0u);
+  }
+}
+
 // Warp-local work queue over [0,total): returns this sub-warp's next item or ~0ull.
 struct WarpQueue {
   unsigned long long next = 0, end = 0;

@@ -28,18 +28,19 @@ namespace {
 // rank_l(v, sp) and rank_l(v, ep) for one level. lv = level base + 32*j. All 32 lanes call it.
 __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp_pos, uint32_t ep_pos,
                                           bool active, int j, uint32_t& rs, uint32_t& re) {
-  const uint32_t pat = v * 0x11111111u;
   const uint32_t ls = sp_pos & ~(kSymsPerLine - 1), le = ep_pos & ~(kSymsPerLine - 1);  // line*128 == byte offset
   const uint32_t os = sp_pos - ls, oe = ep_pos - le;
   const bool split = active && (le != ls);
   Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
   if (active) ks = ldg_nc_v8(lv + ls);
   if (split) ke = ldg_nc_v8(lv + le);
-  const uint32_t hs = chunk_hits(ks, pat);
+  const uint32_t hs = chunk_hits(ks, v);
   const uint32_t cs = chunk_counter(ks, v, j);
   uint32_t he = hs, ce = cs;
   if (__any_sync(0xFFFFFFFFu, split)) {  // warp-uniform: skipped once every interval is narrow
-    const uint32_t h2 = chunk_hits(ke, pat);
+    uint32_t v2 = v;
+    asm("" : "+r"(v2));  // opaque copy: rebuild the four plane masks here instead of keeping them in registers
+    const uint32_t h2 = chunk_hits(ke, v2);
     const uint32_t c2 = chunk_counter(ke, v, j);
     he = split ? h2 : hs;
     ce = split ? c2 : cs;
@@ -63,6 +64,8 @@ template <bool kShortcut, bool kInstr>
 __global__ void __launch_bounds__(kThreads, kShortcut ? CSFM_SHORTCUT_CTAS : 8)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
+  __shared__ uint4 step_tab[256];
+  load_step_table(step_tab, iv.hdr);
   load_tables(tb, iv.hdr);
 
   const int lane = threadIdx.x & 31;
@@ -109,13 +112,14 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   // Sets up the step that prepends byte b to the interval [sp,ep).
   auto begin_step = [&](uint32_t b) {
     if (kInstr) ++my_steps;
-    if (tb.C[b + 1] == tb.C[b]) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
+    const uint4 e = step_tab[b];
+    if (e.y & 0x80000000u) {  // symbol absent: occ(c,.) == 0 -> sp == ep (fm_index.cpp:96)
       finish(0, 0, 0);
       return;
     }
-    code = tb.code_of_byte[b];
-    base = tb.base_by_byte[b];
-    add0 = tb.start1[code >> 4];
+    code = e.y;
+    base = e.x;
+    add0 = e.z;
     if (rem > 1) next_byte = ptr[-1];  // prefetch: in flight during the rank levels
   };
 
@@ -126,6 +130,9 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // the sections its generation is in. A generation is not held up for more than refill_wait
     // trips by a query that keeps stepping.
     bool served;
+    // (the stepping-only variant keeps per-sub-warp refills: batching them was measured to gain
+    // nothing there -- equal-length batches fall into step by themselves -- and its bookkeeping
+    // cost 12 % on the issue-bound C2 workload)
     const uint32_t item = queue_take32(wq, !active, lane, a.cursor, (uint32_t)a.npat,
                                        kShortcut && since_refill < iv.refill_wait ? iv.refill_min : 1u, served);
     if (kShortcut) since_refill = served ? 0u : since_refill + 1u;
@@ -558,7 +565,7 @@ __device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict_
   const uint32_t line = p & ~(kSymsPerLine - 1), off = p - line;
   if (active) k = ldg_nc_v8(lv + line);
   v = __shfl_sync(0xFFFFFFFFu, chunk_symbol(k, off), (lane & ~3) | (int)(off >> 5));
-  return group4_sum(chunk_partial(chunk_counter(k, v, j), chunk_hits(k, v * 0x11111111u), off, j));
+  return group4_sum(chunk_partial(chunk_counter(k, v, j), chunk_hits(k, v), off, j));
 }
 
 // ------------------------------------------------------------------------------------------
