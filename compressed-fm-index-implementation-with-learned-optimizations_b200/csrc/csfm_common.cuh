@@ -14,9 +14,9 @@
 //             hi (a 16-ary wavelet matrix: group g starts at start1[g] = #{codes with hi < g}).
 //   line b of a level = 128 symbols [128b, 128b+128) + 16 absolute counters, as 4 chunks of 32 B:
 //       chunk j : cnt[4j..4j+3] (u32: #symbols == v in the level before this line)
-//                 pay[4j..4j+3] (u32: symbols 32j..32j+31 of the line, 4 bits each, interleaved:
-//                                symbol s of the chunk sits in word s&3, nibble s>>2, so the four
-//                                per-word match masks fold into one hit word in symbol order)
+//                 pay[0..3]     (u32: symbols 32j..32j+31 of the line, bit-sliced: word b holds
+//                                bit b of each symbol, so the symbols equal to v come out as
+//                                one hit word in symbol order after four logic operations)
 //   rank_l(v,p) = line[p>>7].cnt[v] + #{k < (p&127) : sym[k] == v}: ONE line, fetched by a
 //   4-lane sub-warp as four 256-bit loads (one L1 wavefront, four sectors, one DRAM fetch).
 //   nblk = n/128 + 1 so that p == n (ep starts at n) has a line; padding symbols are 0 and are

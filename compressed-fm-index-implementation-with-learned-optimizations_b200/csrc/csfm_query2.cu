@@ -2,7 +2,8 @@
 //
 // Execution model: a 4-lane sub-warp owns one query (count) / one occurrence row (locate). One
 // rank = one 128-byte line = four 256-bit loads (LDG.E.256, one per lane, ONE L1 wavefront), a
-// counter pick, one folded hit word + one masked popc per lane, two xor-shuffles. A byte
+// counter pick, one hit word (four logic ops on the bit-sliced payload) + one masked popc per lane,
+// two xor-shuffles. A byte
 // alphabet needs two dependent line fetches per rank, DNA one.
 //
 // All eight sub-warps of a warp run one loop in lock-step and in PHASE: a loop trip is a whole
