@@ -172,7 +172,7 @@ def planes_from_blob(blob: np.ndarray):
     return n, planes
 
 
-def build_reference_index(fm, text, wl):
+def build_reference_index(fm, text, wl, with_locate=False):
     """UNMODIFIED cs::FMIndex (oracle/_ref) over the same text. The O(n^2 log n) build_sa_naive cannot
     run at this size, so the BWT comes from the GPU builder (untimed setup) and the reference's own
     BitVector::build_from_words builds its rank directory over the bit planes."""
@@ -182,6 +182,9 @@ def build_reference_index(fm, text, wl):
     idx8 = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]),
                                              device=text.device.index, flags=fm.BUILD_NO_COMPACT | fm.BUILD_LAYOUT_BINARY64)
     blob = idx8.blob_to_host()
+    bwt = ssa = None
+    if with_locate:  # the reference's LF reads bwt_[i] and its locate reads ssa_ (fm_index.hpp:62-66, fm_index.cpp:141-152)
+        bwt, ssa = idx8.bwt(), idx8.ssa()
     idx8.close()
     n2, planes = planes_from_blob(blob)
     del blob
@@ -191,7 +194,7 @@ def build_reference_index(fm, text, wl):
         hist += torch.bincount(text[s0: s0 + (1 << 27)].int(), minlength=256).cpu().numpy().astype(np.uint64)
     Carr = np.zeros(257, np.uint32)
     Carr[1:] = np.cumsum(hist).astype(np.uint32)
-    return oracle.RefIndex(planes=planes, C_array=Carr, n=n, stride=wl["stride"])
+    return oracle.RefIndex(planes=planes, C_array=Carr, n=n, stride=wl["stride"], bwt=bwt, ssa=ssa)
 
 
 def reference_timed_sample(ref, data, offs, budget_s, nthreads, min_queries=None):
@@ -267,7 +270,38 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # locate leg (BASELINE.json configs[3]: DNA text, ssa_stride 32, frequent text-sampled patterns)
 # ------------------------------------------------------------------------------------------------
-def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5):
+def locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, budget_s):
+    """The unmodified reference's locate() on the host cores over a bounded sample (a few patterns, small
+    limit: every LF step of the reference rescans whole bit planes), checked against the GPU."""
+    import oracle
+    nthreads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref = build_reference_index(fm, text, {"stride": 32}, with_locate=True)
+    t_inject = time.perf_counter() - t0
+    q, lim = nthreads, 2
+    data = bytes_d[: q * plen].cpu().numpy()
+    offs = offs_d[: q + 1].cpu().numpy().astype(np.uint64)
+    t0 = time.perf_counter()
+    tot, out_n, pos = ref.locate_batch(data, offs, limit=lim, nthreads=nthreads, keep_positions=True)
+    dt = time.perf_counter() - t0
+    rate = tot / max(dt, 1e-9)
+    lim2 = int(min(64, max(lim, rate * budget_s / q)))
+    if lim2 >= 2 * lim:
+        lim = lim2
+        t0 = time.perf_counter()
+        tot, out_n, pos = ref.locate_batch(data, offs, limit=lim, nthreads=nthreads, keep_positions=True)
+        dt = time.perf_counter() - t0
+    g_offs, g_pos, g_status = idx.locate_batch(data, offs, limit=lim)
+    ok = bool((g_status == 0).all()) and int(g_offs[-1]) == int(tot)
+    for k in range(q):
+        ok = ok and bool((g_pos[int(g_offs[k]): int(g_offs[k + 1])] == pos[k * lim: k * lim + int(out_n[k])]).all())
+    return {"value": tot / dt, "unit": "occurrences/s", "cores": nthreads, "kind": "reference",
+            "sample": f"{q} patterns, limit {lim}: {tot} occurrences in {dt:.1f} s on {nthreads} std::threads "
+                      f"(reference index injected in {t_inject:.0f} s)",
+            "bit_exact_vs_gpu": ok}
+
+
+def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5, cpu_budget=0.0):
     """locate_batch on device-resident inputs/outputs: occurrences/s, checked by re-reading the text."""
     import torch
     from csfm_b200 import workloads as w
@@ -326,6 +360,11 @@ def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, ite
                         "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_batch": alg,
                         "note": "sum over occurrences of LF steps x L x line bytes + 32 B sample + 8 B output; time covers count pass + scan + expand + walk"},
            "checks": {"positions_verified_against_text": positions_ok, "all_counts_ge_1": counts_ok, "failed_queries": 0}}
+    if cpu_budget > 0:
+        try:
+            out["cpu_baseline"] = locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, cpu_budget)
+        except Exception as e:  # pragma: no cover
+            out["cpu_baseline"] = {"value": None, "unit": "occurrences/s", "kind": "reference", "sample": f"unavailable: {e!r}"}
     idx.close()
     return out
 
@@ -624,7 +663,7 @@ def run_engine(args, rank, world, local_rank):
         try:
             del d_batches, text
             torch.cuda.empty_cache()
-            locate = measure_locate(fm, dev)
+            locate = measure_locate(fm, dev, cpu_budget=0.0 if args.no_cpu_baseline else min(args.cpu_budget, 10.0))
         except Exception as e:  # pragma: no cover
             locate = {"unavailable": repr(e)}
 
