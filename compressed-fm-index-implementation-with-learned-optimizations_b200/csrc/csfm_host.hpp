@@ -68,6 +68,7 @@ struct csfm_index {
 
   uint32_t instr_mask = 0;
   bool tma_staging = false;  // count kernel variant (csfm_set_option / CSFM_PATTERN_STAGING=tma)
+  bool no_sa_locate = false;  // CSFM_NO_SA_LOCATE: walk even when the index carries its suffix array
   csfm_call_stats stats{};
   std::mutex mu;
 };

@@ -404,11 +404,30 @@ int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs,
 
 // Pass 3+4 of locate: SA rows of every slot, then the LF walks. Asynchronous on `stream`.
 // Uses the intervals left in idx->ws_tmp by locate_plan.
+// Index with the full suffix array on board (text-verification sections: the text ends in a unique
+// smallest byte, so the LF walk from row r ends at (sample + steps) % n == SA[r] and never fails):
+// the position of a row is one gather instead of ~stride LF steps.
+__global__ void rows_to_positions_kernel(const uint32_t* __restrict__ sa, uint64_t* __restrict__ out_pos,
+                                         unsigned long long total) {
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    out_pos[i] = sa[(uint32_t)out_pos[i]];
+}
+
 int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
                 int32_t* d_status, cudaStream_t stream) {
   if (npat == 0 || total == 0) return CSFM_OK;
   const uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
   expand_rows_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(d_row_sp, d_out_offs, npat, d_out_pos);
+  if (idx->view.dense && idx->view.dense_shift == 0 && !idx->no_sa_locate) {
+    const bool timed_sa = (idx->instr_mask & 2u) != 0;
+    if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
+    rows_to_positions_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(idx->view.dense, d_out_pos, total);
+    if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
+    CSFM_CUDA(cudaGetLastError());
+    idx->stats.kernel_launches += 2;
+    return CSFM_OK;
+  }
   unsigned long long* ctr = next_counter_slot(idx);
   CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
   WalkArgs w{};

@@ -430,6 +430,15 @@ def test_text_verification_shortcut(fm, sigma, n):
     c2, se2 = idx.count_batch(d, o, want_intervals=True)
     oc2, ose2 = orc.count_batch(d, o)
     assert (c2 == oc2).all() and (se2 == ose2).all()
+    # locate on an index that carries its suffix array: positions by one gather per row (no LF walk),
+    # same SA-row order, same limit semantics, same positions as the walking index and the oracle
+    for limit in (3, 100000):
+        offs, pos, status = idx.locate_batch(d, o, limit=limit)
+        assert idx.last_call_stats().lf_steps == 0
+        ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=limit)
+        assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
+        poffs, ppos, pstatus = plain.locate_batch(d, o, limit=limit)
+        assert (poffs == ooffs).all() and (ppos == opos).all() and (pstatus == ostatus).all()
 
 
 @pytest.mark.parametrize("copies,sigma", [(2, 200), (3, 60), (4, 30), (7, 120)])
