@@ -301,18 +301,30 @@ def locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, budget_s):
             "bit_exact_vs_gpu": ok}
 
 
-def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5, cpu_budget=0.0):
-    """locate_batch on device-resident inputs/outputs: occurrences/s, checked by re-reading the text."""
+def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5, cpu_budget=0.0):
+    """locate_batch on device-resident inputs/outputs: occurrences/s, checked by re-reading the text.
+
+    Weak scaling like the count leg: rank 0 builds the index, one broadcast replicates it, every rank
+    locates its own `npat` patterns; value = occurrences of all ranks / max over ranks of the device time.
+    Beside it (rank-local, reported by rank 0): the same batch through the host-pointer call
+    csfm_locate_batch (`e2e`) and on an index that keeps its whole suffix array (`resident_sa`)."""
     import torch
+    import torch.distributed as dist
     from csfm_b200 import workloads as w
     n = 1 << n_log2
     text = w.dna_text_torch(n, 6, dev)
-    t0 = time.perf_counter()
-    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index)
-    torch.cuda.synchronize()
-    build_s = time.perf_counter() - t0
+    build_s = bcast_ms = None
+    idx = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+        idx, bcast_ms = fm.parallel.replicate_index(idx, dev, src=0)
     info = idx.info()
-    bytes_d, offs_d = w.sampled_patterns_torch(text, npat, plen, plen, 0, 8)
+    bytes_d, offs_d = w.sampled_patterns_torch(text, npat, plen, plen, 0, 8, first=rank * npat)
     stream = torch.cuda.Stream(device=dev)
     d_offs_out = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
     d_status = torch.zeros(npat, dtype=torch.int32, device=dev)
@@ -320,9 +332,25 @@ def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, ite
                                     d_status.data_ptr(), stream.cuda_stream)
     d_pos = torch.zeros(max(1, total), dtype=torch.int64, device=dev)
 
-    def run():
-        return idx.locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, d_offs_out.data_ptr(),
-                                       d_pos.data_ptr(), total, d_status.data_ptr(), stream.cuda_stream)
+    def run(ix=None, pos=None):
+        return (ix or idx).locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, d_offs_out.data_ptr(),
+                                               (d_pos if pos is None else pos).data_ptr(), total, d_status.data_ptr(),
+                                               stream.cuda_stream)
+
+    def timed(fn, k):
+        for _ in range(2):
+            fn()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(k):
+                fn()
+            e1.record(stream)
+        stream.synchronize()
+        return e0.elapsed_time(e1) / k
 
     idx.set_instrumentation(1)
     run()
@@ -338,28 +366,83 @@ def measure_locate(fm, dev, n_log2=28, npat=200_000, plen=10, limit=100_000, ite
         ok &= text[d_pos[sample] + k] == bytes_d[offs_d[q_of] + k]
     positions_ok = bool(ok.all().item())
     counts_ok = bool(((d_offs_out[1:] - d_offs_out[:-1]) >= 1).all().item())
-    for _ in range(2):
-        run()
-    stream.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(iters):
-            run()
-        e1.record(stream)
-    stream.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    ms = timed(run, iters)
+    ms_local, total_all, lf_all = ms, total, lf_steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([total, lf_steps, int(positions_ok and counts_ok)], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        ms, total_all, lf_all = float(t[0]), int(c[0]), int(c[1])
+        positions_ok = counts_ok = int(c[2]) == world
+    if rank != 0:
+        idx.close()
+        return None
     L, lb = int(info.levels), int(info.line_bytes)
-    alg = lf_steps * L * lb + total * 40
+    alg = lf_all * L * lb + total_all * 40
     peak, _ = measured_peak()
-    out = {"metric": "locate occurrences/sec", "value": total / (ms / 1e3), "unit": "occurrences/s", "ms_per_batch": ms,
-           "config": {"workload": f"C4-style: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen}, limit {limit}",
-                      "levels": L, "line_bytes": lb, "index_bytes": int(info.blob_bytes), "index_build_s": build_s},
-           "occurrences_per_batch": int(total), "lf_steps_per_occurrence": lf_steps / max(1, total),
-           "roofline": {"bound": "hbm", "kernel": "walk_kernel", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_batch": alg,
-                        "note": "sum over occurrences of LF steps x L x line bytes + 32 B sample + 8 B output; time covers count pass + scan + expand + walk"},
+    out = {"metric": "locate occurrences/sec", "value": total_all / (ms / 1e3), "unit": "occurrences/s", "n_gpus": world,
+           "ms_per_batch": ms, "scaling": "weak",
+           "config": {"workload": f"C4-style: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen} per GPU, limit {limit}",
+                      "levels": L, "line_bytes": lb, "index_bytes": int(info.blob_bytes), "index_build_s": build_s,
+                      "index_broadcast_ms": bcast_ms},
+           "occurrences_per_batch": int(total_all), "lf_steps_per_occurrence": lf_all / max(1, total_all),
+           "roofline": {"bound": "hbm", "kernel": "walk2_kernel" if int(info.layout) == 2 else "walk_kernel",
+                        "achieved": alg / world / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / world / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_batch": alg / world,
+                        "note": "per GPU: sum over occurrences of LF steps x L x line bytes + 32 B sample + 8 B output; time covers count "
+                                "pass + scan + expand + walk. Above 1 because about a quarter of the line fetches hit the L2"},
            "checks": {"positions_verified_against_text": positions_ok, "all_counts_ge_1": counts_ok, "failed_queries": 0}}
+
+    # ---- the same batch through the host-pointer call (pinned buffers; H2D and D2H inside the timed region)
+    try:
+        h_bytes = bytes_d.cpu().pin_memory()
+        h_offs = offs_d.cpu().pin_memory()
+        h_out_offs = torch.zeros(npat + 1, dtype=torch.int64).pin_memory()
+        h_pos = torch.zeros(total, dtype=torch.int64).pin_memory()
+        h_status = torch.zeros(npat, dtype=torch.int32).pin_memory()
+        import ctypes
+        tot_c = ctypes.c_uint64()
+        L_ = fm.lib()
+
+        def host_call():
+            rc = L_.csfm_locate_batch(idx._h, h_bytes.data_ptr(), h_offs.data_ptr(), npat, limit, h_out_offs.data_ptr(),
+                                      h_pos.data_ptr(), total, h_status.data_ptr(), ctypes.byref(tot_c))
+            if rc != 0:
+                raise RuntimeError(L_.csfm_last_error().decode())
+
+        host_call()
+        host_call()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            host_call()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / 3
+        out["e2e"] = {"value": total / (e2e_ms / 1e3), "unit": "occurrences/s", "ms_per_batch": e2e_ms, "n_gpus": 1,
+                      "h2d_bytes_per_step": int(h_bytes.numel() + 8 * h_offs.numel()),
+                      "d2h_bytes_per_step": int(8 * total + 8 * (npat + 1) + 4 * npat),
+                      "api": "csfm_locate_batch (host pointers, pinned; positions are 8 B each, so the D2H copy of the "
+                             "result is the larger part of the step)",
+                      "equals_device_path": bool((h_pos.numpy() == d_pos.cpu().numpy()).all())}
+        del h_pos
+    except Exception as e:  # pragma: no cover
+        out["e2e"] = {"unavailable": repr(e)}
+
+    # ---- an index that keeps its whole suffix array (4 n bytes more): a row's position is one gather
+    try:
+        idx_sa = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index,
+                                                   flags=fm.BUILD_FORCE_TEXT_CHECK)
+        d_pos2 = torch.zeros_like(d_pos)
+        ms_sa = timed(lambda: run(idx_sa, d_pos2), iters)
+        out["resident_sa"] = {"value": total / (ms_sa / 1e3), "unit": "occurrences/s", "ms_per_batch": ms_sa, "n_gpus": 1,
+                              "index_bytes": int(idx_sa.info().blob_bytes),
+                              "positions_equal_walk": bool(torch.equal(d_pos, d_pos2)),
+                              "note": "CSFM_BUILD_FORCE_TEXT_CHECK: text + full suffix array ride in the index blob, locate "
+                                      "reads SA[row] instead of walking LF to a sampled row (same positions, same order)"}
+        idx_sa.close()
+        del d_pos2
+    except Exception as e:  # pragma: no cover
+        out["resident_sa"] = {"unavailable": repr(e)}
+
     if cpu_budget > 0:
         try:
             out["cpu_baseline"] = locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, cpu_budget)
@@ -564,6 +647,17 @@ def run_engine(args, rank, world, local_rank):
     stream.synchronize()
     e2e_equal = bool((h_counts.numpy() == d_counts.cpu().numpy()).all())
 
+    # ---- locate leg (every rank takes part: weak scaling like the count leg) ---------------------------
+    locate = None
+    if not args.no_locate:
+        try:
+            locate = measure_locate(fm, dev, rank, world,
+                                    cpu_budget=0.0 if (args.no_cpu_baseline or world > 1) else min(args.cpu_budget, 10.0))
+        except Exception as e:  # pragma: no cover
+            if world > 1:
+                raise  # a rank that drops out of the collectives would hang the others
+            locate = {"unavailable": repr(e)}
+
     # max over ranks
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, e2e_s_u64], dtype=torch.float64, device=dev)
@@ -658,14 +752,6 @@ def run_engine(args, rank, world, local_rank):
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
-    locate = None
-    if world == 1 and not args.no_locate:
-        try:
-            del d_batches, text
-            torch.cuda.empty_cache()
-            locate = measure_locate(fm, dev, cpu_budget=0.0 if args.no_cpu_baseline else min(args.cpu_budget, 10.0))
-        except Exception as e:  # pragma: no cover
-            locate = {"unavailable": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

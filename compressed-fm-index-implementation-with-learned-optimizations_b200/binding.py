@@ -80,6 +80,7 @@ SIGNATURES = {
     "csfm_count_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
     "csfm_count_batch_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_submit32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
+    "csfm_count_batch_submit_len8": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_wait": (C.c_int, [_vp, C.c_uint64]),
     "csfm_locate_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_locate_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp,

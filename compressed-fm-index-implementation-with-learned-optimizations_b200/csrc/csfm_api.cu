@@ -176,6 +176,7 @@ void csfm_destroy(csfm_index* idx) {
     }
     sl.in.release();
     sl.out.release();
+    sl.scan.release();
   }
   if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
   if (idx->d_sa) cudaFree(idx->d_sa);
@@ -379,6 +380,7 @@ int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint6
                             uint64_t* d_counts, uint64_t* d_sp_ep, void* stream) {
   if (!idx || (npat && (!d_offs || !d_counts))) return fail(CSFM_ERR_INVALID, "null argument");
   DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);  // the per-call stats and the cursor ring are shared by all callers of a handle
   begin_call(idx);
   return count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0,
                       static_cast<cudaStream_t>(stream));
@@ -533,6 +535,54 @@ int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint3
   CSFM_CUDA(cudaGetLastError());
   CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
   idx->stats.h2d_bytes = (npat + 1) * 4 + nbytes;
+  idx->stats.d2h_bytes = npat * 4;
+  return CSFM_OK;
+}
+
+int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes, const uint8_t* lens8,
+                                 uint64_t npat, uint32_t* counts32, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!lens8 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  uint64_t sum = 0;  // the kernel trusts the rebuilt offsets: they must stay inside the staged bytes
+  for (uint64_t i = 0; i < npat; ++i) sum += lens8[i];
+  if (sum != nbytes) return fail(CSFM_ERR_INVALID, "nbytes differs from the sum of the pattern lengths");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const uint64_t t = idx->next_ticket++;
+  csfm_index::AsyncSlot& sl = idx->async_slot[t % CSFM_ASYNC_SLOTS];
+  if (!sl.stream) CSFM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+  if (sl.ticket) CSFM_CUDA(cudaStreamSynchronize(sl.stream));  // slot still busy with an older batch
+  sl.ticket = t;
+  *ticket = t;
+  if (npat == 0) return CSFM_OK;
+  // input slot: [offs (npat+1) u64][bytes, 256-byte aligned][lens (npat+1) u8 as copied + a zero, 256-byte aligned]
+  const size_t offs_bytes = (npat + 1) * 8;
+  const size_t bytes_at = (offs_bytes + 255) & ~(size_t)255;
+  const size_t lens_at = (bytes_at + nbytes + 255) & ~(size_t)255;
+  int rc = sl.in.ensure(lens_at + npat + 1 + 512);
+  if (rc) return rc;
+  rc = sl.out.ensure(npat * 8 + npat * 4);  // [counts u64][counts u32]
+  if (rc) return rc;
+  uint64_t* d_offs = sl.in.as<uint64_t>();
+  uint8_t* d_bytes = sl.in.as<uint8_t>() + bytes_at;
+  uint8_t* d_lens = sl.in.as<uint8_t>() + lens_at;
+  uint64_t* d_counts = sl.out.as<uint64_t>();
+  uint32_t* d_counts32 = reinterpret_cast<uint32_t*>(d_counts + npat);
+  CSFM_CUDA(cudaMemcpyAsync(d_lens, lens8, npat, cudaMemcpyHostToDevice, sl.stream));
+  CSFM_CUDA(cudaMemsetAsync(d_lens + npat, 0, 1, sl.stream));  // so that offs[npat] comes out of the same scan
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  rc = offsets_from_lengths8(d_lens, npat + 1, d_offs, sl.scan, sl.stream);
+  if (rc) return rc;
+  const uint32_t saved = idx->instr_mask;
+  idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
+  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, nullptr, nullptr, nullptr, 0, sl.stream);
+  idx->instr_mask = saved;
+  if (rc) return rc;
+  const int grid = (int)std::min<uint64_t>((npat + 255) / 256, (uint64_t)idx->num_sms * 8);
+  narrow_counts_kernel<<<grid, 256, 0, sl.stream>>>(d_counts, d_counts32, npat);
+  CSFM_CUDA(cudaGetLastError());
+  CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
+  idx->stats.h2d_bytes = npat + nbytes;
   idx->stats.d2h_bytes = npat * 4;
   return CSFM_OK;
 }

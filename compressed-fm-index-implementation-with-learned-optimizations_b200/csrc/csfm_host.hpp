@@ -56,7 +56,7 @@ struct csfm_index {
   cudaStream_t aux_stream[2] = {nullptr, nullptr};  // slice pipeline of large host-pointer batches
   struct AsyncSlot {  // csfm_count_batch_submit / _wait
     cudaStream_t stream = nullptr;
-    csfm::DeviceBuffer in, out;
+    csfm::DeviceBuffer in, out, scan;
     uint64_t ticket = 0;  // ticket currently occupying the slot (0 = free)
   } async_slot[CSFM_ASYNC_SLOTS];
   uint64_t next_ticket = 1;
@@ -99,6 +99,9 @@ int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs,
 int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos,
                 uint64_t total, int32_t* d_status, cudaStream_t stream);
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream);
+// d_offs[0..count) = exclusive prefix sum of d_lens[0..count) (u8 lengths -> u64 offsets), on `stream`
+int offsets_from_lengths8(const uint8_t* d_lens, uint64_t count, uint64_t* d_offs, DeviceBuffer& scratch,
+                          cudaStream_t stream);
 unsigned long long* next_counter_slot(csfm_index* idx);
 
 }  // namespace csfm

@@ -456,6 +456,17 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   return CSFM_OK;
 }
 
+int offsets_from_lengths8(const uint8_t* d_lens, uint64_t count, uint64_t* d_offs, DeviceBuffer& scratch,
+                          cudaStream_t stream) {
+  // u8 inputs accumulated into u64 outputs (the init value's type drives the accumulator)
+  size_t tmp_bytes = 0;
+  CSFM_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, d_lens, d_offs, cub::Sum(), (uint64_t)0, (int64_t)count, stream));
+  int rc = scratch.ensure(tmp_bytes + 16);
+  if (rc) return rc;
+  CSFM_CUDA(cub::DeviceScan::ExclusiveScan(scratch.p, tmp_bytes, d_lens, d_offs, cub::Sum(), (uint64_t)0, (int64_t)count, stream));
+  return CSFM_OK;
+}
+
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream) {
   if (idx->h.n == 0) return CSFM_OK;
   const bool nib = idx->view.layout == kLayoutNibble128;

@@ -180,6 +180,13 @@ CSFM_API int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, cons
  * csfm_count_batch_wait; the offsets are widened and the counts narrowed on the device. */
 CSFM_API int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint32_t* offs32,
                                        uint64_t npat, uint32_t* counts32, uint64_t* ticket);
+/* Most compact form: one LENGTH byte per pattern instead of an offset (patterns of at most 255
+ * bytes, packed back to back in `bytes`; nbytes must equal the sum of the lengths, which is
+ * checked: CSFM_ERR_INVALID otherwise). The offsets are rebuilt by a prefix sum on the device, so
+ * 1 + m bytes per pattern cross the bus instead of 4 + m. */
+CSFM_API int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes,
+                                          const uint8_t* lens8, uint64_t npat, uint32_t* counts32,
+                                          uint64_t* ticket);
 CSFM_API int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket);
 CSFM_API int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes,
                                      const uint64_t* d_offs, uint64_t npat, uint64_t* d_counts,

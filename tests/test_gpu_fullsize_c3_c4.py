@@ -1,0 +1,197 @@
+"""GPU, BASELINE.json configs[2] and configs[3] at FULL size, through properties that do not need a CPU
+index of that size (the oracle's restatement at n = 2^30 would take minutes and tens of GB):
+
+  C3  n = 2^30 bytes, sigma = 256, 1 M text-sampled patterns of length 8..32 (the bench workload)
+      * the GPU-built suffix array passes the O(n) certificate (a certified SA is THE reference SA:
+        suffixes are distinct and sais.hpp:13's order is total), BWT and SSA equal their definitions
+        over it (bwt.hpp:10-13, fm_index.cpp:57-65);
+      * the default count kernel (text verification) == the stepping kernel (every character a rank
+        step) on all 1 M patterns, and both report at least one occurrence of every sampled pattern;
+      * count(p) == a naive scan of the text for a sample of patterns (the text ends in a unique
+        smallest byte, so the BWT's cyclic wrap-around cannot add matches);
+      * locate(p) positions, sorted == the naive scan's positions; every position starts an occurrence.
+  C4  n = 2^28 DNA + '$', ssa_stride 32, text-sampled patterns of length 10 (~257 occurrences each)
+      * the same naive-scan checks for count and locate;
+      * sum of the counts == number of located positions (limit above every count);
+      * the LF-walking index and the index with a resident suffix array report identical positions.
+"""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _naive_positions(text, pat):
+    """All start positions of `pat` (1-D uint8 tensor) in `text`, by direct comparison on the device."""
+    import torch
+    n, m = text.numel(), pat.numel()
+    hit = text[: n - m + 1] == pat[0]
+    for k in range(1, m):
+        hit &= text[k: n - m + 1 + k] == pat[k]
+    return torch.nonzero(hit).flatten()
+
+
+def _locate_device(idx, bytes_d, offs_d, npat, limit, dev):
+    import torch
+    offs = torch.zeros(npat + 1, dtype=torch.int64, device=dev)
+    status = torch.zeros(npat, dtype=torch.int32, device=dev)
+    tot = idx.locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, offs.data_ptr(), 0, 0, status.data_ptr())
+    pos = torch.zeros(max(1, tot), dtype=torch.int64, device=dev)
+    idx.locate_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, limit, offs.data_ptr(), pos.data_ptr(), tot,
+                            status.data_ptr())
+    torch.cuda.synchronize()
+    return offs, pos[:tot], status
+
+
+def _positions_are_occurrences(text, bytes_d, offs_d, offs, pos, max_len):
+    import torch
+    tot = pos.numel()
+    q_of = torch.searchsorted(offs, torch.arange(tot, device=pos.device), right=True) - 1
+    lens = (offs_d[1:] - offs_d[:-1])[q_of]
+    ok = torch.ones(tot, dtype=torch.bool, device=pos.device)
+    for k in range(max_len):
+        live = lens > k
+        t = text[torch.where(live, pos + k, torch.zeros_like(pos))]
+        p = bytes_d[torch.where(live, offs_d[q_of] + k, torch.zeros_like(pos))]
+        ok &= (~live) | (t == p)
+    return bool(ok.all().item())
+
+
+@pytest.fixture(scope="module")
+def c3():
+    import torch
+    import csfm_b200 as fm
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n = 1 << 30
+    text = fm.workloads.byte_text_torch(n, 3, dev)
+    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0, flags=fm.BUILD_KEEP_SA)
+    yield fm, dev, text, idx
+    idx.close()
+    del text
+    torch.cuda.empty_cache()
+
+
+def test_c3_build_products_certified(c3):
+    import numpy as np
+    import torch
+    fm, dev, text, idx = c3
+    n = text.numel()
+    info = idx.info()
+    assert info.levels == 2 and info.line_bytes == 128 and info.sigma == 256 and info.text_check == 1
+    cert = fm.workloads.certify_sa_torch(text, idx.sa_device_ptr(), n)
+    assert cert["ok"], cert
+
+    class _Mem:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    sa = torch.as_tensor(_Mem(idx.sa_device_ptr(), 4 * n), device=dev).view(torch.int32)
+    # SSA: samples[k] = SA[k * stride]  (fm_index.cpp:57-65)
+    assert (idx.ssa() == sa[::32].contiguous().cpu().numpy().view(np.uint32)).all()
+    # BWT[i] = T[(SA[i] - 1) mod n]  (bwt.hpp:10-13), compared in 2^27-row pieces
+    bwt = torch.from_numpy(idx.bwt())
+    for lo in range(0, n, 1 << 27):
+        s = sa[lo: lo + (1 << 27)].to(torch.int64) & 0xFFFFFFFF
+        want = text[(s - 1) % n]
+        assert torch.equal(want.cpu(), bwt[lo: lo + (1 << 27)])
+    # C[c] = number of symbols smaller than c  (fm_index.cpp:36-47)
+    hist = torch.zeros(256, dtype=torch.int64, device=dev)
+    for lo in range(0, n, 1 << 27):
+        hist += torch.bincount(text[lo: lo + (1 << 27)].int(), minlength=256)
+    C = np.zeros(257, np.uint32)
+    C[1:] = np.cumsum(hist.cpu().numpy()).astype(np.uint32)
+    assert (idx.C_array() == C).all()
+    idx.release_sa()
+    torch.cuda.empty_cache()
+
+
+def test_c3_one_million_counts(c3):
+    import torch
+    fm, dev, text, idx = c3
+    npat = 1_000_000
+    bytes_d, offs_d = fm.workloads.sampled_patterns_torch(text, npat, 8, 32, 4, 5)
+    fast = torch.zeros(npat, dtype=torch.int64, device=dev)
+    plain = torch.zeros(npat, dtype=torch.int64, device=dev)
+    spep = torch.zeros(2 * npat, dtype=torch.int64, device=dev)
+    idx.set_instrumentation(1)
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, fast.data_ptr(), 0)
+    torch.cuda.synchronize()
+    st = idx.last_call_stats()
+    assert st.text_checks > 0.9 * npat           # the verification kernel really ran
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, plain.data_ptr(), spep.data_ptr())
+    torch.cuda.synchronize()
+    assert idx.last_call_stats().text_checks == 0  # asking for the intervals selects the stepping kernel
+    idx.set_instrumentation(0)
+    assert torch.equal(fast, plain)
+    assert bool((fast >= 1).all())
+    se = spep.view(-1, 2)
+    assert torch.equal(se[:, 1] - se[:, 0], plain)   # the interval of a non-empty result has `count` rows
+    # count and locate against a naive scan of the text
+    offs, pos, status = _locate_device(idx, bytes_d, offs_d, 4096, 100000, dev)
+    assert int(status.max()) == 0
+    assert torch.equal(offs[1:] - offs[:-1], fast[:4096])
+    assert _positions_are_occurrences(text, bytes_d, offs_d, offs, pos, 32)
+    for q in range(0, 24):
+        pat = bytes_d[int(offs_d[q]): int(offs_d[q + 1])]
+        want = _naive_positions(text, pat)
+        assert int(fast[q]) == want.numel()
+        got = pos[int(offs[q]): int(offs[q + 1])]
+        assert torch.equal(torch.sort(got).values, want)
+    # short patterns (length 1..3) have many occurrences and stay in the stepping path
+    short = [text[5:6], text[100:102], text[1000:1003]]
+    sb = torch.cat(short)
+    so = torch.tensor([0, 1, 3, 6], dtype=torch.int64, device=dev)
+    sc = torch.zeros(3, dtype=torch.int64, device=dev)
+    idx.count_batch_device(sb.data_ptr(), so.data_ptr(), 3, sc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    for k, pat in enumerate(short):
+        assert int(sc[k]) == _naive_positions(text, pat).numel()
+
+
+@pytest.fixture(scope="module")
+def c4():
+    import torch
+    import csfm_b200 as fm
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    n = 1 << 28
+    text = fm.workloads.dna_text_torch(n, 6, dev)
+    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0)
+    yield fm, dev, text, idx
+    idx.close()
+    del text
+    torch.cuda.empty_cache()
+
+
+def test_c4_locate_full_size(c4):
+    import torch
+    fm, dev, text, idx = c4
+    n = text.numel()
+    info = idx.info()
+    assert info.levels == 1 and info.ssa_stride == 32 and info.nsamp == n // 32
+    npat, plen = 50_000, 10
+    bytes_d, offs_d = fm.workloads.sampled_patterns_torch(text, npat, plen, plen, 0, 8)
+    counts = torch.zeros(npat, dtype=torch.int64, device=dev)
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, counts.data_ptr(), 0)
+    offs, pos, status = _locate_device(idx, bytes_d, offs_d, npat, 100000, dev)
+    assert int(status.max()) == 0
+    assert int(counts.max()) < 100000 and int(counts.sum()) == pos.numel()
+    assert torch.equal(offs[1:] - offs[:-1], counts)
+    assert _positions_are_occurrences(text, bytes_d, offs_d, offs, pos, plen)
+    for q in range(16):
+        want = _naive_positions(text, bytes_d[q * plen: (q + 1) * plen])
+        assert int(counts[q]) == want.numel()
+        assert torch.equal(torch.sort(pos[int(offs[q]): int(offs[q + 1])]).values, want)
+    # `limit` keeps the FIRST rows of the interval (fm_index.cpp:118-120)
+    offs5, pos5, _ = _locate_device(idx, bytes_d, offs_d, 1000, 5, dev)
+    for q in range(0, 1000, 97):
+        k = min(5, int(counts[q]))
+        assert int(offs5[q + 1] - offs5[q]) == k
+        assert torch.equal(pos5[int(offs5[q]): int(offs5[q + 1])], pos[int(offs[q]): int(offs[q]) + k])
+    # the index that carries its whole suffix array reads SA[row]: same positions, same order
+    idx_sa = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0,
+                                               flags=fm.BUILD_FORCE_TEXT_CHECK)
+    assert idx_sa.info().text_check == 1
+    offs2, pos2, status2 = _locate_device(idx_sa, bytes_d, offs_d, npat, 100000, dev)
+    assert torch.equal(offs2, offs) and torch.equal(pos2, pos) and int(status2.max()) == 0
+    idx_sa.close()
