@@ -598,13 +598,26 @@ def run_engine(args, rank, world, local_rank):
         h_offs32.append(o32)
     h_out32 = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
 
-    def e2e_run(nsteps, compact):
+    # most compact form (csfm_count_batch_submit_len8): one length byte per pattern in, u32 counts out
+    h_lens8 = []
+    for hb, ho in h_batches:
+        ln = (ho[1:] - ho[:-1])
+        assert int(ln.max()) <= 255
+        l8 = torch.empty(ln.numel(), dtype=torch.uint8).pin_memory()
+        l8.copy_(ln.to(torch.uint8))
+        h_lens8.append(l8)
+    h_out8 = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
+
+    def e2e_run(nsteps, form):
         tickets = []
         for i in range(nsteps):
             hb, ho = h_batches[i % NB]
             if i >= DEPTH:
                 idx.count_batch_wait(tickets[i - DEPTH])  # frees output buffer i % DEPTH
-            if compact:
+            if form == "len8":
+                tickets.append(idx.count_batch_submit_len8(hb.data_ptr(), hb.numel(), h_lens8[i % NB].data_ptr(), batch,
+                                                           h_out8[i % DEPTH].data_ptr()))
+            elif form == "u32":
                 tickets.append(idx.count_batch_submit32(hb.data_ptr(), h_offs32[i % NB].data_ptr(), batch, h_out32[i % DEPTH].data_ptr()))
             else:
                 tickets.append(idx.count_batch_submit(hb.data_ptr(), ho.data_ptr(), batch, h_out[i % DEPTH].data_ptr()))
@@ -612,21 +625,24 @@ def run_engine(args, rank, world, local_rank):
             idx.count_batch_wait(t)
 
     e2e_steps = args.steps
-    e2e_times = {}
-    for compact in (False, True):
-        e2e_run(max(3, args.warmup), compact)
+    e2e_times, e2e_bytes = {}, {}
+    for form in ("u64", "u32", "len8"):
+        e2e_run(max(3, args.warmup), form)
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        e2e_run(e2e_steps, compact)
+        e2e_run(e2e_steps, form)
         torch.cuda.synchronize()
-        e2e_times[compact] = time.perf_counter() - t0
+        e2e_times[form] = time.perf_counter() - t0
         barrier()
-        if compact:
-            st32 = idx.last_call_stats()
-            h2d32, d2h32 = int(st32.h2d_bytes), int(st32.d2h_bytes)
-    e2e_s, e2e_s_u64 = e2e_times[True], e2e_times[False]
-    compact_equal = bool((h_out32[(e2e_steps - 1) % DEPTH].numpy().astype(np.int64) == h_out[(e2e_steps - 1) % DEPTH].numpy()).all())
+        stf = idx.last_call_stats()
+        e2e_bytes[form] = (int(stf.h2d_bytes), int(stf.d2h_bytes))
+    h2d32, d2h32 = e2e_bytes["len8"]
+    e2e_s_u32 = e2e_times["u32"]
+    e2e_s, e2e_s_u64 = e2e_times["len8"], e2e_times["u64"]
+    last = (e2e_steps - 1) % DEPTH
+    compact_equal = bool((h_out32[last].numpy().astype(np.int64) == h_out[last].numpy()).all() and
+                         (h_out8[last].numpy().astype(np.int64) == h_out[last].numpy()).all())
     h_counts = h_out[(e2e_steps - 1) % DEPTH]
     # the synchronous call (csfm_count_batch) for comparison: one step at a time, nothing overlapped
     h_sync = torch.zeros(batch, dtype=torch.int64).pin_memory()
@@ -660,9 +676,9 @@ def run_engine(args, rank, world, local_rank):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, e2e_s_u64], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_s_u64, e2e_s_u32], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, e2e_s_u64 = float(t[0]), float(t[1]), float(t[2])
+        total_ms, e2e_s, e2e_s_u64, e2e_s_u32 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         return
 
@@ -765,8 +781,12 @@ def run_engine(args, rank, world, local_rank):
                    "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"])},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": "csfm_count_batch_submit32/_wait (host pointers, pinned, u32 offsets and counts, 3 steps in flight)",
-                "kernels_per_step": 3,
+                "api": "csfm_count_batch_submit_len8/_wait (host pointers, pinned, one length byte per pattern in, u32 counts "
+                       "out, 3 steps in flight)",
+                "kernels_per_step": 4,
+                "u32_api": {"value": world * e2e_steps * batch / e2e_s_u32, "ms_per_step": 1e3 * e2e_s_u32 / e2e_steps,
+                            "h2d_bytes_per_step": e2e_bytes["u32"][0], "d2h_bytes_per_step": e2e_bytes["u32"][1],
+                            "api": "csfm_count_batch_submit32/_wait (u32 offsets and counts)"},
                 "u64_api": {"value": world * e2e_steps * batch / e2e_s_u64, "ms_per_step": 1e3 * e2e_s_u64 / e2e_steps,
                             "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
                             "api": "csfm_count_batch_submit/_wait (u64 offsets and counts)"},

@@ -328,6 +328,13 @@ class FMIndex:
         _check(lib().csfm_count_batch_submit32(self._h, _vp(bytes_ptr), _vp(offs32_ptr), npat, _vp(counts32_ptr), C.byref(t)))
         return int(t.value)
 
+    def count_batch_submit_len8(self, bytes_ptr: int, nbytes: int, lens8_ptr: int, npat: int, counts32_ptr: int) -> int:
+        """Most compact asynchronous count: one length byte per pattern in, u32 counts out."""
+        t = C.c_uint64()
+        _check(lib().csfm_count_batch_submit_len8(self._h, _vp(bytes_ptr), nbytes, _vp(lens8_ptr), npat, _vp(counts32_ptr),
+                                                  C.byref(t)))
+        return int(t.value)
+
     def count_batch_wait(self, ticket: int):
         _check(lib().csfm_count_batch_wait(self._h, ticket))
 

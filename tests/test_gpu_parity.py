@@ -387,6 +387,38 @@ def test_async_submit32_compact(fm, force_text):
         assert (got.astype(np.uint64) == oc).all()
 
 
+@pytest.mark.parametrize("force_text", [False, True])
+def test_async_submit_len8(fm, force_text):
+    """csfm_count_batch_submit_len8: one length byte per pattern in (offsets rebuilt by a device prefix sum),
+    u32 counts out; empty patterns, 255-byte patterns, an empty batch and a wrong nbytes."""
+    import torch
+    rng = np.random.default_rng(78)
+    text, alpha = _rand_text(rng, 120_000, 60, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16), flags=fm.BUILD_FORCE_TEXT_CHECK if force_text else 0)
+    orc = oracle.OracleIndex(text, stride=16)
+    jobs = []
+    for k in range(6):
+        pats = _mixed_patterns(rng, text, alpha, 2500 + 77 * k, 24)
+        pats += [b"", text[1000:1255].tobytes(), text[-255:].tobytes(), b""]
+        if k == 4:
+            pats = [b""]
+        d, o = fm.pack_patterns(pats)
+        npat = o.size - 1
+        hb = torch.from_numpy(d.copy()).pin_memory() if d.size else torch.zeros(1, dtype=torch.uint8).pin_memory()
+        hl = torch.from_numpy(np.diff(o).astype(np.uint8)).pin_memory()
+        hc = torch.full((npat,), -1, dtype=torch.int32).pin_memory()
+        t = idx.count_batch_submit_len8(hb.data_ptr(), int(o[-1]), hl.data_ptr(), npat, hc.data_ptr())
+        jobs.append((t, d, o, hb, hl, hc))
+    for t, d, o, hb, hl, hc in jobs:
+        idx.count_batch_wait(t)
+        oc, _ = orc.count_batch(d, o)
+        assert (hc.numpy().view(np.uint32).astype(np.uint64) == oc).all()
+    t, d, o, hb, hl, hc = jobs[0]
+    with pytest.raises(fm.CsfmError):
+        idx.count_batch_submit_len8(hb.data_ptr(), int(o[-1]) + 1, hl.data_ptr(), o.size - 1, hc.data_ptr())
+    idx.count_batch_wait(idx.count_batch_submit_len8(0, 0, 0, 0, 0))  # empty batch: a ticket, no work
+
+
 @pytest.mark.parametrize("sigma,n", [(4, 300_000), (255, 400_000), (20, 50_000)])
 def test_text_verification_shortcut(fm, sigma, n):
     """Counts WITHOUT intervals take the shortcut: once a query's interval is a single row, its
