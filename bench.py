@@ -337,11 +337,11 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
                                                (d_pos if pos is None else pos).data_ptr(), total, d_status.data_ptr(),
                                                stream.cuda_stream)
 
-    def timed(fn, k):
+    def timed(fn, k, all_ranks=True):
         for _ in range(2):
             fn()
         stream.synchronize()
-        if world > 1:
+        if world > 1 and all_ranks:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
@@ -432,7 +432,7 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
         idx_sa = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index,
                                                    flags=fm.BUILD_FORCE_TEXT_CHECK)
         d_pos2 = torch.zeros_like(d_pos)
-        ms_sa = timed(lambda: run(idx_sa, d_pos2), iters)
+        ms_sa = timed(lambda: run(idx_sa, d_pos2), iters, all_ranks=False)  # rank 0 only
         out["resident_sa"] = {"value": total / (ms_sa / 1e3), "unit": "occurrences/s", "ms_per_batch": ms_sa, "n_gpus": 1,
                               "index_bytes": int(idx_sa.info().blob_bytes),
                               "positions_equal_walk": bool(torch.equal(d_pos, d_pos2)),
