@@ -479,7 +479,8 @@ def run_engine(args, rank, world, local_rank):
     if rank == 0:
         t0 = time.perf_counter()
         idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank,
-                                                flags=fm.BUILD_LAYOUT_BINARY64 if args.layout == 1 else 0)
+                                                flags=(fm.BUILD_LAYOUT_BINARY64 if args.layout == 1 else 0) |
+                                                (fm.BUILD_LARGE_TABLE if args.large_table else 0))
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
     if world > 1:
@@ -581,6 +582,59 @@ def run_engine(args, rank, world, local_rank):
                     "table_lookups_per_launch": plain_lookups, "counts_equal_default_kernel": plain_equal}
         launches += K2 + 4
         del d_spep
+
+    # ---- the same batches on an index built with a LARGE k-mer table budget (opt-in, CSFM_BUILD_LARGE_TABLE):
+    # for a byte alphabet k goes from 3 to 4 (2^32 entries, 34 GB), the lookup leaves ~1 row and the query
+    # goes straight to the text verification: one table line + one suffix-array line + one text line
+    large = None
+    if world == 1 and not args.no_large_table and not args.large_table and int(info.layout) == 2 and torch.cuda.mem_get_info()[0] > 100e9:
+        try:
+            t0 = time.perf_counter()
+            idx_big = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank,
+                                                        flags=fm.BUILD_LARGE_TABLE)
+            torch.cuda.synchronize()
+            big_build_s = time.perf_counter() - t0
+            binfo = idx_big.info()
+            d_counts_big = torch.zeros(batch, dtype=torch.int64, device=dev)
+
+            def step_big(b):
+                bytes_d, offs_d = d_batches[b % NB]
+                idx_big.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), batch, d_counts_big.data_ptr(), 0, stream.cuda_stream)
+
+            idx_big.set_instrumentation(1)
+            step_big(0)
+            stream.synchronize()
+            bst = idx_big.last_call_stats()
+            big_steps, big_lookups, big_checks = int(bst.search_steps), int(bst.table_lookups), int(bst.text_checks)
+            idx_big.set_instrumentation(0)
+            big_equal = bool((d_counts_big.cpu().numpy() == c0).all())
+            K3 = min(args.steps, 100)
+            for i in range(3):
+                step_big(i)
+            stream.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(K3):
+                step_big(i)
+            e1.record(stream)
+            stream.synchronize()
+            big_ms = e0.elapsed_time(e1) / K3
+            big_bytes = big_steps * 2 * L * int(info.line_bytes) + big_lookups * 128 + big_checks * 256
+            large = {"build_flag": "CSFM_BUILD_LARGE_TABLE", "kmer_k": int(binfo.kmer_k), "index_bytes": int(binfo.blob_bytes),
+                     "index_build_s": big_build_s, "ms_per_launch": big_ms, "launches_timed": K3,
+                     "queries_per_s": batch / (big_ms / 1e3), "search_steps_per_launch": big_steps,
+                     "table_lookups_per_launch": big_lookups, "text_checks_per_launch": big_checks,
+                     "algorithmic_bytes_per_launch": big_bytes, "achieved_gbs": big_bytes / (big_ms / 1e3) / 1e9,
+                     "counts_equal_default_index": big_equal,
+                     "note": "opt-in build: the k-mer table takes up to 40 GiB of the 180 GB (k = 4 on bytes, 13 on DNA+$), a query is "
+                             "three dependent fetches (table, suffix array, text); fewer executed bytes per query, so a lower "
+                             "bandwidth figure at a higher q/s"}
+            launches += K3 + 4
+            idx_big.close()
+            del d_counts_big
+            torch.cuda.empty_cache()
+        except Exception as e:  # pragma: no cover
+            large = {"unavailable": repr(e)}
 
     # ---- timed region 2: end to end through the host-pointer C ABI ------------------------------------
     # The streaming form of the public API (csfm_count_batch_submit / _wait): every step copies its
@@ -738,6 +792,10 @@ def run_engine(args, rank, world, local_rank):
         stepping["note"] = ("the same batches through the plain backward-search kernel (every character a rank step; "
                             "selected by asking for the intervals), for comparison with the default kernel above")
         roofline["stepping_only"] = stepping
+    if large:
+        if "achieved_gbs" in large:
+            large["frac"] = large["achieved_gbs"] / peak
+        roofline["large_kmer_table"] = large
     if traffic:
         # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)
         roofline["dram_gbs_from_traffic"] = traffic / (total_ms / args.steps / 1e3) / 1e9
@@ -778,7 +836,8 @@ def run_engine(args, rank, world, local_rank):
                    "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
                    "l2_policy": f"inputs larger than L2: {info.blob_bytes / 1e9:.2f} GB index + a different 28 MB batch every step" if n >= (1 << 29)
                    else "index is L2-resident at this size; a different batch every step",
-                   "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"])},
+                   "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"]),
+                   "build_flags": "CSFM_BUILD_LARGE_TABLE" if args.large_table else "default"},
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": "csfm_count_batch_submit_len8/_wait (host pointers, pinned, one length byte per pattern in, u32 counts "
@@ -813,6 +872,8 @@ def main():
     ap.add_argument("--layout", type=int, default=2, choices=[1, 2], help="2 = 16-ary levels / 128-byte lines (default), 1 = binary / 64-byte lines")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--large-table", action="store_true", help="build the MAIN index with CSFM_BUILD_LARGE_TABLE (opt-in mode)")
+    ap.add_argument("--no-large-table", action="store_true", help="skip the leg on an index with a 34 GB k-mer table")
     ap.add_argument("--no-locate", action="store_true", help="skip the locate leg (occurrences/s on a C4-style index)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -329,7 +329,7 @@ int index_finish_handle(csfm_index* idx) {
   v.dense_shift = h.dense_shift;
   // a verification costs two HBM fetches and three loop trips; a step costs `levels` fetches and
   // one trip: worth it from 3 characters left on a two-level index, from 8 on a one-level index
-  v.verify_min = h.levels >= 2 ? 3u : 8u;
+  v.verify_min = h.verify_min ? h.verify_min : (h.levels >= 2 ? 3u : 8u);
   if (const char* e = std::getenv("CSFM_VERIFY_MIN")) v.verify_min = (uint32_t)std::atoi(e);
   idx->no_sa_locate = std::getenv("CSFM_NO_SA_LOCATE") != nullptr;
   v.refill_min = 8;
@@ -393,10 +393,19 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   if (nib && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
     const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : h.sigma;
     uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
+    if (flags & CSFM_BUILD_LARGE_TABLE) {
+      // opt-in: spend device memory on the table so that the lookup itself leaves few rows and the
+      // query goes straight to the text verification (k = 4 for a byte alphabet at n = 2^30: 34 GB;
+      // k = 13 for DNA+$ at n = 2^26: 9.8 GB)
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+      budget = std::max<uint64_t>(budget, std::min<uint64_t>(40ull << 30, free_b / 3));
+    }
     if (const char* e = std::getenv("CSFM_KMER_BUDGET_MB")) budget = (uint64_t)std::max(1, std::atoi(e)) << 20;
     uint32_t k = 0;
     uint64_t entries = 1;
-    while (radix >= 2 && entries * radix * 8 <= budget && k < 16) {
+    // a key that already leaves a quarter of a row on average gains nothing from another character
+    while (radix >= 2 && entries * radix * 8 <= budget && k < 16 && entries < 4 * n) {
       entries *= radix;
       ++k;
     }
@@ -418,6 +427,11 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // plain vs 2.37e9 with the verification variant that never fires. So: two levels, in HBM.
   const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
   if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
+  if (flags & CSFM_BUILD_LARGE_TABLE) {
+    // after a long key little is left to step through: verify from three characters on, whatever the level count
+    flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
+    h.verify_min = 3;
+  }
   if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
       ((levels_in_hbm && L == 2) || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
     uint8_t last = 0;

@@ -79,7 +79,8 @@ struct BlobHeader {
   uint64_t off_text;           // 0 = absent; n bytes + 64 bytes of padding, 16-byte aligned
   uint64_t off_dense;          // u32 samples
   uint32_t dense_shift;        // samples at rows that are multiples of 1 << dense_shift
-  uint32_t reserved0[5];
+  uint32_t verify_min;         // 0 = by level count (3 / 8); else: verify once at least this many characters are left
+  uint32_t reserved0[4];
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47

@@ -172,8 +172,17 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           finish(ep - sp, sp, ep);
         } else {
           rem = (uint32_t)(m - kk);
-          ptr = a.bytes + (o1 - 1 - kk);
-          begin_step(*ptr);
+          ptr = a.bytes + (o1 - kk);  // the last character the lookup consumed
+          if (shortcut && ep - sp <= max_rows && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+            // a long table key already leaves few rows: verify them without a rank step
+            next_byte = ptr[-1];
+            if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
+            vstage = 1;
+            if (kInstr) ++my_checks;
+          } else {
+            --ptr;
+            begin_step(*ptr);
+          }
         }
       } else {
         // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])

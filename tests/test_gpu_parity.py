@@ -419,6 +419,36 @@ def test_async_submit_len8(fm, force_text):
     idx.count_batch_wait(idx.count_batch_submit_len8(0, 0, 0, 0, 0))  # empty batch: a ticket, no work
 
 
+@pytest.mark.parametrize("sigma,n,term", [(4, 300_000, True), (255, 400_000, True), (20, 50_000, True), (4, 100_000, False)])
+def test_large_table_build(fm, sigma, n, term):
+    """CSFM_BUILD_LARGE_TABLE: a long k-mer key, then straight to the text verification (no rank step when
+    the lookup already leaves at most four rows). Same counts, intervals and positions as the oracle;
+    without a unique terminator the flag only enlarges the table."""
+    rng = np.random.default_rng(sigma * 11 + n)
+    text, alpha = _rand_text(rng, n, sigma, term)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=8), flags=fm.BUILD_LARGE_TABLE)
+    info = idx.info()
+    assert info.text_check == (1 if term else 0)
+    small = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=8))
+    assert info.kmer_k >= small.info().kmer_k
+    orc = oracle.OracleIndex(text, stride=8)
+    pats = _mixed_patterns(rng, text, alpha, 30_000, 40)
+    pats += [text[s:s + m].tobytes() for m in range(1, 12) for s in (0, 1, n // 2, n - m)]
+    d, o = fm.pack_patterns(pats)
+    idx.set_instrumentation(1)
+    counts = idx.count_batch(d, o)
+    if term:
+        assert idx.last_call_stats().text_checks > 0
+    idx.set_instrumentation(0)
+    oc, ose = orc.count_batch(d, o)
+    assert (counts == oc).all()
+    c2, se = idx.count_batch(d, o, want_intervals=True)
+    assert (c2 == oc).all() and (se == ose).all()
+    offs, pos, status = idx.locate_batch(d, o, limit=20)
+    ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=20)
+    assert (offs == ooffs).all() and (status == ostatus).all() and (pos == opos).all()
+
+
 @pytest.mark.parametrize("sigma,n", [(4, 300_000), (255, 400_000), (20, 50_000)])
 def test_text_verification_shortcut(fm, sigma, n):
     """Counts WITHOUT intervals take the shortcut: once a query's interval is a single row, its
