@@ -795,6 +795,13 @@ def run_engine(args, rank, world, local_rank):
     if large:
         if "achieved_gbs" in large:
             large["frac"] = large["achieved_gbs"] / peak
+            try:
+                t3 = json.load(open(tp)).get(args.workload + "_large_table", {}).get("dram_bytes_per_launch")
+            except Exception:
+                t3 = None
+            if t3:
+                large["traffic"] = t3
+                large["frac_of_random_fetch_ceiling"] = t3 / 128 / (large["ms_per_launch"] / 1e3) / 37.3e9
         roofline["large_kmer_table"] = large
     if traffic:
         # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)

@@ -28,7 +28,7 @@ texts = st.one_of(
 
 @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(text=texts, stride=st.sampled_from([1, 2, 3, 4, 7, 32, 1000]), limit=st.sampled_from([1, 2, 5, 100000]),
-       flags=st.sampled_from([0, 1, 4, 5, 8, 32, 33, 40]), seed=st.integers(0, 2**31 - 1), terminate=st.booleans())
+       flags=st.sampled_from([0, 1, 4, 5, 8, 32, 33, 40, 64, 65]), seed=st.integers(0, 2**31 - 1), terminate=st.booleans())
 def test_engine_equals_oracle(fm, text, stride, limit, flags, seed, terminate):
     if terminate:
         text = text + b"\x00"
