@@ -516,13 +516,14 @@ def run_engine(args, rank, world, local_rank):
 
     # exact executed-step counts per batch (S of the roofline model) + correctness properties
     idx.set_instrumentation(1)
-    steps_per_batch, lookups_per_batch, checks_per_batch = [], [], []
+    steps_per_batch, lookups_per_batch, checks_per_batch, halves_per_batch = [], [], [], []
     for b in range(NB):
         step_device(b)
         stream.synchronize()
         steps_per_batch.append(int(idx.last_call_stats().search_steps))
         lookups_per_batch.append(int(idx.last_call_stats().table_lookups))
         checks_per_batch.append(int(idx.last_call_stats().text_checks))
+        halves_per_batch.append(int(idx.last_call_stats().half_steps))
         if b == 0:
             c0 = d_counts.cpu().numpy().copy()
             assert (c0 >= 1).all(), "text-sampled patterns must occur at least once"
@@ -744,8 +745,8 @@ def run_engine(args, rank, world, local_rank):
     line_bytes = int(info.line_bytes)
     # executed traffic model: every rank step reads 2 x L lines, every k-mer table lookup one line,
     # every text verification two (the suffix-array entry and the text window)
-    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + lookups_per_batch[i % NB] * 128 + checks_per_batch[i % NB] * 256
-                 for i in range(args.steps)]
+    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + halves_per_batch[i % NB] * 2 * line_bytes +
+                 lookups_per_batch[i % NB] * 128 + checks_per_batch[i % NB] * 256 for i in range(args.steps)]
     achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
@@ -763,6 +764,8 @@ def run_engine(args, rank, world, local_rank):
                 "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
                 "table_lookups_per_launch": float(np.mean([lookups_per_batch[i % NB] for i in range(args.steps)])),
                 "text_checks_per_launch": float(np.mean([checks_per_batch[i % NB] for i in range(args.steps)])),
+                "half_steps_per_launch": float(np.mean([halves_per_batch[i % NB] for i in range(args.steps)])),
+                "half_table": int(info.half_table),
                 "kmer_k": int(info.kmer_k), "text_check": int(info.text_check),
                 "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
                 "note": "duration per launch = CUDA events on the launching stream around each step "

@@ -48,13 +48,13 @@ class IndexInfo(C.Structure):
     _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("levels", C.c_uint32), ("ssa_stride", C.c_uint32),
                 ("device", C.c_uint32), ("nsamp", C.c_uint64), ("blocks_per_level", C.c_uint64),
                 ("blob_bytes", C.c_uint64), ("has_sa", C.c_uint32), ("layout", C.c_uint32), ("line_bytes", C.c_uint32),
-                ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("half_table", C.c_uint32)]
 
 
 class CallStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("search_steps", C.c_uint64), ("lf_steps", C.c_uint64), ("kernel_ms", C.c_float),
-                ("table_lookups", C.c_uint32), ("text_checks", C.c_uint32), ("reserved", C.c_uint32)]
+                ("table_lookups", C.c_uint32), ("text_checks", C.c_uint32), ("half_steps", C.c_uint32)]
 
 
 # name -> (restype, argtypes): every symbol include/csfm.h declares

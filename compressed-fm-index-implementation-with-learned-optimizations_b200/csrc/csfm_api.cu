@@ -211,6 +211,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;
   out->kmer_k = idx->view.kmer_k;
   out->text_check = idx->view.text != nullptr;
+  out->half_table = idx->view.kmer_hi != nullptr;
   return CSFM_OK;
 }
 
@@ -303,6 +304,8 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
     if (!nib || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
         h.off_kmer + entries * 8 > h.total_bytes)
       return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
+    if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + entries * 8 || h.off_kmer_hi + entries * 128 > h.total_bytes))
+      return fail(CSFM_ERR_FORMAT, "inconsistent half-step table in blob header");
   }
   auto* idx = new (std::nothrow) csfm_index();
   if (!idx) return fail(CSFM_ERR_NOMEM, "host allocation failed");
@@ -366,6 +369,7 @@ static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
       idx->stats.search_steps = hp[8];
       idx->stats.table_lookups = (uint32_t)hp[10];
       idx->stats.text_checks = (uint32_t)hp[11];
+      idx->stats.half_steps = (uint32_t)hp[12];
     }
   }
   if (idx->instr_mask & 2u) {
@@ -688,6 +692,7 @@ int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out) {
     if (!out->search_steps) out->search_steps = hp[8];
     if (!out->table_lookups) out->table_lookups = (uint32_t)hp[10];
     if (!out->text_checks) out->text_checks = (uint32_t)hp[11];
+    if (!out->half_steps) out->half_steps = (uint32_t)hp[12];
     if (!out->lf_steps) out->lf_steps = hp[9];
   }
   if ((idx->instr_mask & 2u) && out->kernel_ms == 0.f) {

@@ -324,6 +324,8 @@ int index_finish_handle(csfm_index* idx) {
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
+  v.kmer_hi = (h.kmer_k && h.off_kmer_hi) ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer_hi) : nullptr;
+  if (std::getenv("CSFM_NO_HALF_TABLE")) v.kmer_hi = nullptr;  // experiment knob: ignore a table that is present
   v.text = h.off_text ? idx->d_blob + h.off_text : nullptr;
   v.dense = h.off_text ? reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_dense) : nullptr;
   v.dense_shift = h.dense_shift;
@@ -339,6 +341,7 @@ int index_finish_handle(csfm_index* idx) {
   if (std::getenv("CSFM_NO_TEXT_CHECK")) v.text = nullptr;  // experiment knob: ignore the sections
   if (std::getenv("CSFM_NO_KMER_TABLE")) {  // experiment knob: ignore a table that is present
     v.kmer = nullptr;
+    v.kmer_hi = nullptr;
     v.kmer_k = 0;
   }
   for (int l = 0; l < (int)kMaxLevels; ++l) v.zeros[l] = h.zeros[l];
@@ -346,8 +349,8 @@ int index_finish_handle(csfm_index* idx) {
   if (!idx->ev0) CSFM_CUDA(cudaEventCreate(&idx->ev0));
   if (!idx->ev1) CSFM_CUDA(cudaEventCreate(&idx->ev1));
   if (!idx->d_counters) {
-    CSFM_CUDA(cudaMalloc(&idx->d_counters, kCounterSlots * 4 * sizeof(unsigned long long)));
-    CSFM_CUDA(cudaMemset(idx->d_counters, 0, kCounterSlots * 4 * sizeof(unsigned long long)));
+    CSFM_CUDA(cudaMalloc(&idx->d_counters, kCounterSlots * kCounterWords * sizeof(unsigned long long)));
+    CSFM_CUDA(cudaMemset(idx->d_counters, 0, kCounterSlots * kCounterWords * sizeof(unsigned long long)));
   }
   if (!idx->h_pinned) CSFM_CUDA(cudaHostAlloc(&idx->h_pinned, 4096, cudaHostAllocDefault));
   return CSFM_OK;
@@ -414,6 +417,14 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
       h.kmer_radix = (uint32_t)radix;
       h.off_kmer = h.total_bytes;
       h.total_bytes = align_up(h.off_kmer + entries * 8, 256);
+      // half-step table: 16 entries per k-mer; kept when it is no larger than the levels themselves
+      // (C3: k = 3, 2.1 GB beside 2.3 GB of levels) and the table is not already a large one
+      const uint64_t hi_bytes = entries * 16 * 8;
+      if (L == 2 && !(flags & CSFM_BUILD_LARGE_TABLE) && hi_bytes <= std::max<uint64_t>((uint64_t)L * h.level_stride, 32ull << 20) &&
+          hi_bytes <= (4ull << 30) && !std::getenv("CSFM_BUILD_NO_HALF_TABLE")) {
+        h.off_kmer_hi = h.total_bytes;
+        h.total_bytes = align_up(h.off_kmer_hi + hi_bytes, 256);
+      }
     }
   }
   // Text-verification shortcut: needs the text and its suffix array, and a text whose last byte

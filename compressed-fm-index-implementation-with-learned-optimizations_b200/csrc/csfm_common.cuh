@@ -80,7 +80,12 @@ struct BlobHeader {
   uint64_t off_dense;          // u32 samples
   uint32_t dense_shift;        // samples at rows that are multiples of 1 << dense_shift
   uint32_t verify_min;         // 0 = by level count (3 / 8); else: verify once at least this many characters are left
-  uint32_t reserved0[4];
+  // half-step table (two-level layout 2): for every k-mer e and every high nibble g, the interval
+  // of the k-mer mapped through level 0 for g, i.e. (start1[g] + rank_0(g, sp), start1[g] + rank_0(g, ep)),
+  // at entry e * 16 + g. A query with more than k characters starts from it and needs only the
+  // level-1 half of its first rank step. 0 = absent.
+  uint64_t off_kmer_hi;
+  uint32_t reserved0[2];
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
@@ -101,6 +106,7 @@ struct IndexView {
   const uint32_t* ssa;
   const BlobHeader* hdr;  // device pointer (tables are staged to shared memory per CTA)
   const uint2* kmer;      // k-mer jump table or nullptr
+  const uint2* kmer_hi;   // half-step table or nullptr
   const uint8_t* text;    // text for the verification shortcut or nullptr
   const uint32_t* dense;  // SA[k << dense_shift]
   uint32_t kmer_k;

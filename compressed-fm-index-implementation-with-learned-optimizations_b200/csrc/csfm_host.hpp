@@ -75,7 +75,8 @@ struct csfm_index {
 
 namespace csfm {
 
-constexpr uint32_t kCounterSlots = 256;  // each slot = 4 x u64
+constexpr uint32_t kCounterSlots = 256;
+constexpr uint32_t kCounterWords = 8;  // u64 per slot: work cursor, rank steps, table lookups, text checks, half steps
 
 // csfm_build.cu
 // d_text / d_sa (both nullable): when given and the text ends in a unique smallest byte, they are
@@ -84,7 +85,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
                           uint32_t stride, int device, uint32_t flags, csfm_index** out,
                           const uint8_t* d_text = nullptr, const uint32_t* d_sa = nullptr);
 int index_finish_handle(csfm_index* idx);  // fills view/stream/workspace after d_blob + h are set
-int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: fills the table section
+int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: fills the table sections
 // csfm_sa.cu
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,

@@ -307,7 +307,7 @@ int persistent_grid(const csfm_index* idx, const void* kernel) {
 
 unsigned long long* next_counter_slot(csfm_index* idx) {
   const uint32_t s = idx->counter_slot++ % kCounterSlots;
-  return idx->d_counters + (size_t)s * 4;
+  return idx->d_counters + (size_t)s * kCounterWords;
 }
 
 int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
@@ -328,7 +328,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
     return CSFM_OK;
   }
   unsigned long long* ctr = next_counter_slot(idx);
-  CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
+  CSFM_CUDA(cudaMemsetAsync(ctr, 0, kCounterWords * sizeof(unsigned long long), stream));
   CountArgs a{};
   a.bytes = d_bytes;
   a.offs = d_offs;
@@ -356,7 +356,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   idx->stats.kernel_launches += 1;
   if (a.steps_total) {  // ctr[1] = rank steps, ctr[2] = k-mer table lookups
     CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 8, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
-    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 10, ctr + 2, 16, cudaMemcpyDeviceToHost, stream));
+    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 10, ctr + 2, 24, cudaMemcpyDeviceToHost, stream));  // + ctr[4] = half steps
   }
   return CSFM_OK;
 }
@@ -429,7 +429,7 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
     return CSFM_OK;
   }
   unsigned long long* ctr = next_counter_slot(idx);
-  CSFM_CUDA(cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned long long), stream));
+  CSFM_CUDA(cudaMemsetAsync(ctr, 0, kCounterWords * sizeof(unsigned long long), stream));
   WalkArgs w{};
   w.out_pos = d_out_pos;
   w.total = total;

@@ -93,8 +93,10 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   uint32_t rem = 0;              // characters left including the current one
   uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
   uint32_t vstage = 0, vp = 0;   // 0 searching, 1 suffix-array entry requested, 2 windows in flight
-  uint32_t my_steps = 0, my_lookups = 0, my_checks = 0;
+  uint32_t my_steps = 0, my_lookups = 0, my_checks = 0, my_halves = 0;
   uint32_t since_refill = 0;     // warp-uniform: trips since this warp last took queries
+  bool pre = false;              // sp/ep already hold the level-1 interval of the pending step (half-step table)
+  const uint2* const kmer_hi = kShortcut ? iv.kmer_hi : nullptr;  // the plain variant stays within 32 registers
 
   auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
     if (j == 0) {
@@ -163,6 +165,25 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         }
         if (kInstr) ++my_lookups;
         uint2 se = make_uint2(0, 0);
+        if (kmer_hi != nullptr && m > kk) {
+          // half-step table: the k-mer's interval already mapped through level 0 for the high nibble
+          // of the character in front of it; the pending step needs only its level-1 rank
+          ptr = a.bytes + (o1 - 1 - kk);
+          rem = (uint32_t)(m - kk);
+          const uint4 st = step_tab[*ptr];
+          if (present && !(st.y & 0x80000000u)) se = kmer_hi[(size_t)e * 16u + (st.y >> 4)];
+          sp = se.x;
+          ep = se.y;
+          if (sp >= ep) {  // the k-mer, the character, or that nibble inside the interval does not occur
+            finish(0, 0, 0);
+          } else {
+            if (kInstr) ++my_halves;
+            code = st.y;
+            base = st.x;
+            if (rem > 1) next_byte = ptr[-1];
+            pre = true;
+          }
+        } else {
         if (present) se = iv.kmer[e];
         sp = se.x;
         ep = se.y;
@@ -183,6 +204,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
             --ptr;
             begin_step(*ptr);
           }
+        }
         }
       } else {
         // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
@@ -254,13 +276,16 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     const bool ranking = active && vstage == 0;
     if (kShortcut && !__any_sync(0xFFFFFFFFu, ranking)) continue;  // a trip of verifications only
     uint32_t rs, re, s1 = sp, e1 = ep;  // sp and ep themselves must survive a trip spent in verification
-    if (two) {
-      rank_pair(lv0, code >> 4, sp, ep, ranking, j, rs, re);
-      s1 = add0 + rs;
-      e1 = add0 + re;
+    if (two && (!kShortcut || __any_sync(0xFFFFFFFFu, ranking && !pre))) {
+      rank_pair(lv0, code >> 4, sp, ep, ranking && !pre, j, rs, re);
+      if (!pre) {
+        s1 = add0 + rs;
+        e1 = add0 + re;
+      }
     }
     rank_pair(lv_last, code & 15u, s1, e1, ranking, j, rs, re);
     if (ranking) {
+      pre = false;
       sp = base + rs;  // fm_index.cpp:92-93
       ep = base + re;
       if (sp >= ep) {
@@ -281,15 +306,18 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
   }
   if (kInstr && a.steps_total) {
-    unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0, u = (j == 0) ? my_checks : 0;
+    unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0, u = (j == 0) ? my_checks : 0,
+             v = (j == 0) ? my_halves : 0;
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
       t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
       u += __shfl_xor_sync(0xFFFFFFFFu, u, o);
+      v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     }
     if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
     if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
     if (lane == 0 && u) atomicAdd(a.steps_total + 2, (unsigned long long)u);
+    if (lane == 0 && v) atomicAdd(a.steps_total + 3, (unsigned long long)v);
   }
 }
 
@@ -333,6 +361,40 @@ kmer_build_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tabl
       alive = act && sp < ep;
     }
     if (valid && j == 0) table[e] = alive ? make_uint2(sp, ep) : make_uint2(0u, 0u);
+  }
+}
+
+// Fills the half-step table from the finished k-mer table: entry e * 16 + g = the interval of k-mer e
+// mapped through level 0 for the high nibble g. The two lines of an interval are loaded once and
+// serve all 16 nibbles.
+__global__ void __launch_bounds__(kThreads)
+kmer_hi_build_kernel(const __grid_constant__ IndexView iv, const uint2* __restrict__ table, uint2* __restrict__ table_hi,
+                     unsigned long long entries) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int j = threadIdx.x & 3;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const unsigned long long group = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const unsigned long long ngroups = ((unsigned long long)gridDim.x * blockDim.x) >> 2;
+  const unsigned long long trips = (entries + ngroups - 1) / ngroups;
+  for (unsigned long long t = 0; t < trips; ++t) {
+    const unsigned long long e = t * ngroups + group;
+    const bool valid = e < entries;
+    const uint2 se = valid ? table[e] : make_uint2(0u, 0u);
+    const bool alive = valid && se.x < se.y;
+    const uint32_t ls = se.x & ~(kSymsPerLine - 1), le = se.y & ~(kSymsPerLine - 1);
+    Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
+    if (alive) {
+      ks = ldg_nc_v8(lv0 + ls);
+      ke = ldg_nc_v8(lv0 + le);
+    }
+#pragma unroll 1
+    for (uint32_t g = 0; g < 16; ++g) {
+      const uint32_t rs = group4_sum(chunk_partial(chunk_counter(ks, g, j), chunk_hits(ks, g), se.x - ls, j));
+      const uint32_t re = group4_sum(chunk_partial(chunk_counter(ke, g, j), chunk_hits(ke, g), se.y - le, j));
+      if (valid && j == 0)
+        table_hi[e * 16 + g] = (alive && rs < re) ? make_uint2(tb.start1[g] + rs, tb.start1[g] + re) : make_uint2(0u, 0u);
+    }
   }
 }
 
@@ -731,9 +793,16 @@ int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
   const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm((const void*)kmer_build_kernel));
   IndexView v = idx->view;  // the table is being written: the builder itself must not consult it
   v.kmer = nullptr;
+  v.kmer_hi = nullptr;
   v.kmer_k = 0;
   kmer_build_kernel<<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
   CSFM_CUDA(cudaGetLastError());
+  if (h.off_kmer_hi) {
+    uint2* table_hi = reinterpret_cast<uint2*>(idx->d_blob + h.off_kmer_hi);
+    const int grid_hi = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm((const void*)kmer_hi_build_kernel));
+    kmer_hi_build_kernel<<<grid_hi, kThreads, 0, stream>>>(v, table, table_hi, entries);
+    CSFM_CUDA(cudaGetLastError());
+  }
   CSFM_CUDA(cudaStreamSynchronize(stream));
   return CSFM_OK;
 }

@@ -105,7 +105,8 @@ typedef struct {
   uint32_t line_bytes; /* bytes fetched per rank per level: 64 or 128 */
   uint32_t kmer_k;     /* length of the k-mer jump table's keys, 0 = no table */
   uint32_t text_check; /* 1 = text + suffix array resident for the verification shortcut */
-  uint32_t reserved;
+  uint32_t half_table; /* 1 = half-step table resident (two-level indexes: the first rank step of a
+                          query needs only its second level) */
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */
@@ -120,7 +121,8 @@ typedef struct {
                                not in search_steps); 0 unless asked */
   uint32_t text_checks;     /* queries finished by comparing their remaining characters with the
                                text (those characters are not in search_steps); 0 unless asked */
-  uint32_t reserved;
+  uint32_t half_steps;      /* first steps taken from the half-step table: one level (2 lines) instead
+                               of two; not in search_steps; 0 unless asked */
 } csfm_call_stats;
 
 CSFM_API const char* csfm_last_error(void);
