@@ -75,6 +75,7 @@ SIGNATURES = {
     "csfm_extract_bwt": (C.c_int, [_vp, _vp]),
     "csfm_blob": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "csfm_attach_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "csfm_replicate": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "csfm_blob_to_host": (C.c_int, [_vp, _vp, C.c_uint64]),
     "csfm_from_host_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
     "csfm_count_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp]),
@@ -195,6 +196,12 @@ class FMIndex:
         idx = FMIndex(h)
         idx._keepalive = keepalive
         return idx
+
+    def replicate(self, device: int) -> "FMIndex":
+        """A second handle over its own copy of the blob on `device` (csfm_replicate)."""
+        h = _vp()
+        _check(lib().csfm_replicate(self._h, int(device), C.byref(h)))
+        return FMIndex(h, text=self._text)
 
     @staticmethod
     def from_host_blob(blob: np.ndarray, device: int = 0) -> "FMIndex":

@@ -324,6 +324,33 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   return CSFM_OK;
 }
 
+int csfm_replicate(const csfm_index* idx, int device, csfm_index** out) {
+  if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard g(device);
+  if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
+  if (device != idx->device) {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, idx->device) == cudaSuccess && can) {
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(idx->device, 0);
+      if (pe != cudaSuccess) (void)cudaGetLastError();  // already enabled, or not possible: the copy below still works
+    }
+  }
+  void* d = nullptr;
+  CSFM_CUDA(cudaMalloc(&d, idx->blob_bytes));
+  const cudaError_t e = device == idx->device ? cudaMemcpy(d, idx->d_blob, idx->blob_bytes, cudaMemcpyDeviceToDevice)
+                                              : cudaMemcpyPeer(d, device, idx->d_blob, idx->device, idx->blob_bytes);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(CSFM_ERR_CUDA, std::string("replicate: ") + cudaGetErrorString(e));
+  }
+  rc = csfm_attach_blob(d, idx->blob_bytes, device, 1, out);
+  if (rc) cudaFree(d);
+  return rc;
+}
+
 int csfm_blob_to_host(const csfm_index* idx, void* out, uint64_t bytes) {
   if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
   if (bytes < idx->blob_bytes) return fail(CSFM_ERR_CAPACITY, "host buffer smaller than the blob");
@@ -450,43 +477,6 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   return end_call(idx, st, false);
 }
 
-int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
-                            uint64_t* sp_ep, uint64_t* ticket) {
-  if (!idx || !ticket || (npat && (!offs || !counts))) return fail(CSFM_ERR_INVALID, "null argument");
-  const uint64_t nbytes = npat ? offs[npat] : 0;
-  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
-  DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lk(idx->mu);
-  const uint64_t t = idx->next_ticket++;
-  csfm_index::AsyncSlot& sl = idx->async_slot[t % CSFM_ASYNC_SLOTS];
-  if (!sl.stream) CSFM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-  if (sl.ticket) CSFM_CUDA(cudaStreamSynchronize(sl.stream));  // slot still busy with an older batch
-  sl.ticket = t;
-  *ticket = t;
-  if (npat == 0) return CSFM_OK;
-  const size_t offs_bytes = (npat + 1) * 8;
-  int rc = sl.in.ensure(offs_bytes + nbytes + 512);
-  if (rc) return rc;
-  rc = sl.out.ensure(npat * 8 * (sp_ep ? 3 : 1));
-  if (rc) return rc;
-  uint64_t* d_offs = sl.in.as<uint64_t>();
-  uint8_t* d_bytes = sl.in.as<uint8_t>() + ((offs_bytes + 255) & ~(size_t)255);  // aligned: TMA / cp.async staging
-  uint64_t* d_counts = sl.out.as<uint64_t>();
-  uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
-  CSFM_CUDA(cudaMemcpyAsync(d_offs, offs, offs_bytes, cudaMemcpyHostToDevice, sl.stream));
-  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
-  const uint32_t saved = idx->instr_mask;
-  idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
-  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, sl.stream);
-  idx->instr_mask = saved;
-  if (rc) return rc;
-  CSFM_CUDA(cudaMemcpyAsync(counts, d_counts, npat * 8, cudaMemcpyDeviceToHost, sl.stream));
-  if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, sl.stream));
-  idx->stats.h2d_bytes = offs_bytes + nbytes;
-  idx->stats.d2h_bytes = npat * 8 * (sp_ep ? 3 : 1);
-  return CSFM_OK;
-}
-
 namespace {
 __global__ void widen_offsets_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, uint64_t count) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
@@ -496,13 +486,15 @@ __global__ void narrow_counts_kernel(const uint64_t* __restrict__ in, uint32_t* 
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
     out[i] = (uint32_t)in[i];
 }
-}  // namespace
 
-int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint32_t* offs32, uint64_t npat,
-                              uint32_t* counts32, uint64_t* ticket) {
-  if (!idx || !ticket || (npat && (!offs32 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
-  const uint64_t nbytes = npat ? offs32[npat] : 0;
-  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+// How a streaming batch describes where its patterns start.
+enum class PatternIndex { kOffsets64, kOffsets32, kLengths8 };
+
+// The three submit entry points differ only in how the pattern boundaries arrive and how wide the
+// counts leave: one slot, one stream, H2D copies -> (offsets rebuilt on the device) -> count kernel ->
+// (counts narrowed) -> D2H copy. Exactly one of counts64 / counts32 is set.
+int submit_batch(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes, PatternIndex kind, const void* index,
+                 uint64_t npat, uint64_t* counts64, uint64_t* sp_ep, uint32_t* counts32, uint64_t* ticket) {
   DeviceGuard g(idx->device);
   std::lock_guard<std::mutex> lk(idx->mu);
   const uint64_t t = idx->next_ticket++;
@@ -512,35 +504,80 @@ int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint3
   sl.ticket = t;
   *ticket = t;
   if (npat == 0) return CSFM_OK;
-  // input slot: [offs (npat+1) u64][bytes, 256-byte aligned][offs32 as copied, 256-byte aligned]
+  // input slot: [offs (npat+1) u64][bytes, 256-byte aligned: TMA / cp.async staging][compact index as copied, 256-byte aligned]
   const size_t offs_bytes = (npat + 1) * 8;
   const size_t bytes_at = (offs_bytes + 255) & ~(size_t)255;
-  const size_t offs32_at = (bytes_at + nbytes + 255) & ~(size_t)255;
-  int rc = sl.in.ensure(offs32_at + (npat + 1) * 4 + 512);
+  const size_t compact_at = (bytes_at + nbytes + 255) & ~(size_t)255;
+  const size_t compact_bytes = kind == PatternIndex::kOffsets32 ? (npat + 1) * 4 : kind == PatternIndex::kLengths8 ? npat + 1 : 0;
+  int rc = sl.in.ensure(compact_at + compact_bytes + 512);
   if (rc) return rc;
-  rc = sl.out.ensure(npat * 8 + npat * 4);  // [counts u64][counts u32]
+  rc = sl.out.ensure(npat * 8 * (sp_ep ? 3 : 1) + (counts32 ? npat * 4 : 0));  // [counts u64][sp_ep][counts u32]
   if (rc) return rc;
   uint64_t* d_offs = sl.in.as<uint64_t>();
   uint8_t* d_bytes = sl.in.as<uint8_t>() + bytes_at;
-  uint32_t* d_offs32 = reinterpret_cast<uint32_t*>(sl.in.as<uint8_t>() + offs32_at);
+  uint8_t* d_compact = sl.in.as<uint8_t>() + compact_at;
   uint64_t* d_counts = sl.out.as<uint64_t>();
-  uint32_t* d_counts32 = reinterpret_cast<uint32_t*>(d_counts + npat);
-  CSFM_CUDA(cudaMemcpyAsync(d_offs32, offs32, (npat + 1) * 4, cudaMemcpyHostToDevice, sl.stream));
-  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  uint64_t* d_sp_ep = sp_ep ? d_counts + npat : nullptr;
+  uint32_t* d_counts32 = reinterpret_cast<uint32_t*>(d_counts + npat * (sp_ep ? 3 : 1));
   const int grid = (int)std::min<uint64_t>((npat + 1 + 255) / 256, (uint64_t)idx->num_sms * 8);
-  widen_offsets_kernel<<<grid, 256, 0, sl.stream>>>(d_offs32, d_offs, npat + 1);
-  CSFM_CUDA(cudaGetLastError());
+  // all host->device copies first: a kernel between two copies would make the second copy wait until that
+  // kernel has found room beside the persistent count kernel of another slot
+  switch (kind) {
+    case PatternIndex::kOffsets64:
+      CSFM_CUDA(cudaMemcpyAsync(d_offs, index, offs_bytes, cudaMemcpyHostToDevice, sl.stream));
+      idx->stats.h2d_bytes = offs_bytes + nbytes;
+      break;
+    case PatternIndex::kOffsets32:
+      CSFM_CUDA(cudaMemcpyAsync(d_compact, index, (npat + 1) * 4, cudaMemcpyHostToDevice, sl.stream));
+      idx->stats.h2d_bytes = (npat + 1) * 4 + nbytes;
+      break;
+    case PatternIndex::kLengths8:
+      CSFM_CUDA(cudaMemcpyAsync(d_compact, index, npat, cudaMemcpyHostToDevice, sl.stream));
+      CSFM_CUDA(cudaMemsetAsync(d_compact + npat, 0, 1, sl.stream));  // so that offs[npat] comes out of the same scan
+      idx->stats.h2d_bytes = npat + nbytes;
+      break;
+  }
+  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  if (kind == PatternIndex::kOffsets32) {
+    widen_offsets_kernel<<<grid, 256, 0, sl.stream>>>(reinterpret_cast<const uint32_t*>(d_compact), d_offs, npat + 1);
+    CSFM_CUDA(cudaGetLastError());
+  } else if (kind == PatternIndex::kLengths8) {
+    rc = offsets_from_lengths8(d_compact, npat + 1, d_offs, sl.scan, sl.stream);
+    if (rc) return rc;
+  }
   const uint32_t saved = idx->instr_mask;
   idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
-  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, nullptr, nullptr, nullptr, 0, sl.stream);
+  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, d_sp_ep, nullptr, nullptr, 0, sl.stream);
   idx->instr_mask = saved;
   if (rc) return rc;
-  narrow_counts_kernel<<<grid, 256, 0, sl.stream>>>(d_counts, d_counts32, npat);
-  CSFM_CUDA(cudaGetLastError());
-  CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
-  idx->stats.h2d_bytes = (npat + 1) * 4 + nbytes;
-  idx->stats.d2h_bytes = npat * 4;
+  if (counts32) {
+    narrow_counts_kernel<<<grid, 256, 0, sl.stream>>>(d_counts, d_counts32, npat);
+    CSFM_CUDA(cudaGetLastError());
+    CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
+    idx->stats.d2h_bytes = npat * 4;
+  } else {
+    CSFM_CUDA(cudaMemcpyAsync(counts64, d_counts, npat * 8, cudaMemcpyDeviceToHost, sl.stream));
+    if (sp_ep) CSFM_CUDA(cudaMemcpyAsync(sp_ep, d_sp_ep, npat * 16, cudaMemcpyDeviceToHost, sl.stream));
+    idx->stats.d2h_bytes = npat * 8 * (sp_ep ? 3 : 1);
+  }
   return CSFM_OK;
+}
+}  // namespace
+
+int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
+                            uint64_t* sp_ep, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!offs || !counts))) return fail(CSFM_ERR_INVALID, "null argument");
+  const uint64_t nbytes = npat ? offs[npat] : 0;
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  return submit_batch(idx, bytes, nbytes, PatternIndex::kOffsets64, offs, npat, counts, sp_ep, nullptr, ticket);
+}
+
+int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint32_t* offs32, uint64_t npat,
+                              uint32_t* counts32, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!offs32 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
+  const uint64_t nbytes = npat ? offs32[npat] : 0;
+  if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  return submit_batch(idx, bytes, nbytes, PatternIndex::kOffsets32, offs32, npat, nullptr, nullptr, counts32, ticket);
 }
 
 int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes, const uint8_t* lens8,
@@ -550,45 +587,7 @@ int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t
   uint64_t sum = 0;  // the kernel trusts the rebuilt offsets: they must stay inside the staged bytes
   for (uint64_t i = 0; i < npat; ++i) sum += lens8[i];
   if (sum != nbytes) return fail(CSFM_ERR_INVALID, "nbytes differs from the sum of the pattern lengths");
-  DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lk(idx->mu);
-  const uint64_t t = idx->next_ticket++;
-  csfm_index::AsyncSlot& sl = idx->async_slot[t % CSFM_ASYNC_SLOTS];
-  if (!sl.stream) CSFM_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-  if (sl.ticket) CSFM_CUDA(cudaStreamSynchronize(sl.stream));  // slot still busy with an older batch
-  sl.ticket = t;
-  *ticket = t;
-  if (npat == 0) return CSFM_OK;
-  // input slot: [offs (npat+1) u64][bytes, 256-byte aligned][lens (npat+1) u8 as copied + a zero, 256-byte aligned]
-  const size_t offs_bytes = (npat + 1) * 8;
-  const size_t bytes_at = (offs_bytes + 255) & ~(size_t)255;
-  const size_t lens_at = (bytes_at + nbytes + 255) & ~(size_t)255;
-  int rc = sl.in.ensure(lens_at + npat + 1 + 512);
-  if (rc) return rc;
-  rc = sl.out.ensure(npat * 8 + npat * 4);  // [counts u64][counts u32]
-  if (rc) return rc;
-  uint64_t* d_offs = sl.in.as<uint64_t>();
-  uint8_t* d_bytes = sl.in.as<uint8_t>() + bytes_at;
-  uint8_t* d_lens = sl.in.as<uint8_t>() + lens_at;
-  uint64_t* d_counts = sl.out.as<uint64_t>();
-  uint32_t* d_counts32 = reinterpret_cast<uint32_t*>(d_counts + npat);
-  CSFM_CUDA(cudaMemcpyAsync(d_lens, lens8, npat, cudaMemcpyHostToDevice, sl.stream));
-  CSFM_CUDA(cudaMemsetAsync(d_lens + npat, 0, 1, sl.stream));  // so that offs[npat] comes out of the same scan
-  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
-  rc = offsets_from_lengths8(d_lens, npat + 1, d_offs, sl.scan, sl.stream);
-  if (rc) return rc;
-  const uint32_t saved = idx->instr_mask;
-  idx->instr_mask = 0;  // per-call instrumentation is a property of the synchronous entry points
-  rc = count_device(idx, d_bytes, d_offs, npat, d_counts, nullptr, nullptr, nullptr, 0, sl.stream);
-  idx->instr_mask = saved;
-  if (rc) return rc;
-  const int grid = (int)std::min<uint64_t>((npat + 255) / 256, (uint64_t)idx->num_sms * 8);
-  narrow_counts_kernel<<<grid, 256, 0, sl.stream>>>(d_counts, d_counts32, npat);
-  CSFM_CUDA(cudaGetLastError());
-  CSFM_CUDA(cudaMemcpyAsync(counts32, d_counts32, npat * 4, cudaMemcpyDeviceToHost, sl.stream));
-  idx->stats.h2d_bytes = npat + nbytes;
-  idx->stats.d2h_bytes = npat * 4;
-  return CSFM_OK;
+  return submit_batch(idx, bytes, nbytes, PatternIndex::kLengths8, lens8, npat, nullptr, nullptr, counts32, ticket);
 }
 
 int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket) {

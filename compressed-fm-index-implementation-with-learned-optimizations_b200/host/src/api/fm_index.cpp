@@ -4,7 +4,9 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <stdexcept>
+#include <thread>
 
 #include "../../../../include/csfm.h"
 #include "../serialization/csidx.hpp"
@@ -44,6 +46,10 @@ void pack(const std::vector<std::string_view>& pats, std::vector<uint8_t>& bytes
 void FMIndex::set_default_device(int device) { g_default_device = device; }
 
 FMIndex FMIndex::build_from_text(const std::string& text, const BuildParams& p) {
+  return build_from_text(text, p, CSFM_BUILD_DEFAULT);
+}
+
+FMIndex FMIndex::build_from_text(const std::string& text, const BuildParams& p, uint32_t csfm_build_flags) {
   FMIndex idx;
   idx.meta_.n = text.size();
   idx.text_ = std::make_shared<const std::string>(text);
@@ -55,7 +61,7 @@ FMIndex FMIndex::build_from_text(const std::string& text, const BuildParams& p) 
     const bool timers = std::getenv("CS_TIMERS") != nullptr;
     std::unique_ptr<ScopeTimer> t(timers ? new ScopeTimer("build_from_text(gpu)") : nullptr);
     if (csfm_build_from_text(reinterpret_cast<const uint8_t*>(text.data()), text.size(), &cp, default_device(),
-                             CSFM_BUILD_DEFAULT, &h) != CSFM_OK)
+                             csfm_build_flags, &h) != CSFM_OK)
       throw_last("build_from_text");
   }
   idx.handle_ = std::shared_ptr<csfm_index>(h, [](csfm_index* x) { csfm_destroy(x); });
@@ -70,6 +76,42 @@ int FMIndex::device() const {
   csfm_index_info info;
   if (!handle_ || csfm_info(handle_.get(), &info) != CSFM_OK) return -1;
   return static_cast<int>(info.device);
+}
+
+FMIndex FMIndex::replicate_to(int device) const {
+  if (!handle_) throw std::runtime_error("replicate_to: index not built");
+  csfm_index* h = nullptr;
+  if (csfm_replicate(handle_.get(), device, &h) != CSFM_OK) throw_last("replicate_to");
+  FMIndex r;
+  r.meta_ = meta_;
+  r.text_ = text_;
+  r.handle_ = std::shared_ptr<csfm_index>(h, [](csfm_index* x) { csfm_destroy(x); });
+  return r;
+}
+
+void FMIndex::count_batch_sharded(const std::vector<FMIndex>& replicas, const uint8_t* bytes, const uint64_t* offs,
+                                  uint64_t npat, uint64_t* counts) {
+  if (replicas.empty()) throw std::runtime_error("count_batch_sharded: no replicas");
+  const uint64_t world = replicas.size();
+  std::vector<std::thread> workers;
+  std::vector<std::exception_ptr> errors(world);
+  for (uint64_t r = 0; r < world; ++r) {
+    const uint64_t lo = npat * r / world, hi = npat * (r + 1) / world;
+    if (hi == lo) continue;
+    workers.emplace_back([&, r, lo, hi] {
+      try {
+        // a slice keeps the batch's absolute offsets: rebase them so that the slice is a batch of its own
+        std::vector<uint64_t> local(hi - lo + 1);
+        for (uint64_t i = lo; i <= hi; ++i) local[i - lo] = offs[i] - offs[lo];
+        replicas[r].count_batch(bytes + offs[lo], local.data(), hi - lo, counts + lo);
+      } catch (...) {
+        errors[r] = std::current_exception();
+      }
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (auto& e : errors)
+    if (e) std::rethrow_exception(e);
 }
 
 void FMIndex::count_batch(const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,

@@ -38,6 +38,8 @@ class FMIndex {
 public:
   /// fm_index.cpp:16-69 — SA, BWT, C, rank structure and sampled SA, all built on the GPU.
   static FMIndex build_from_text(const std::string& text, const BuildParams& p);
+  /// Same, with CSFM_BUILD_* flags of include/csfm.h (e.g. CSFM_BUILD_LARGE_TABLE, CSFM_BUILD_FORCE_TEXT_CHECK).
+  static FMIndex build_from_text(const std::string& text, const BuildParams& p, uint32_t csfm_build_flags);
   /// fm_index.cpp:71-73 — throws std::runtime_error("on-disk open not implemented yet").
   static FMIndex open_directory(const std::string& dir);
 
@@ -55,6 +57,15 @@ public:
   void count_batch(const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
                    uint64_t* sp_ep = nullptr) const;
   LocateBatch locate_batch(const std::vector<std::string_view>& patterns, size_t limit = 100000) const;
+
+  // ---- more than one GPU in one process (new) -----------------------------------------------
+  /// A replica on another device: the device index is copied there (NVLink peer copy where possible);
+  /// the host-side text is shared. One process per GPU with a broadcast is the other way (parallel.py).
+  FMIndex replicate_to(int device) const;
+  /// Packed count over several replicas: the batch is cut into contiguous slices, one per replica, each
+  /// slice counted on its replica's device from its own host thread. Results as from count_batch.
+  static void count_batch_sharded(const std::vector<FMIndex>& replicas, const uint8_t* bytes, const uint64_t* offs,
+                                  uint64_t npat, uint64_t* counts);
 
   // ---- persistence (new): the reference's .csidx container (src/serialization/serialization.hpp)
   /// Writes TEXT, BWT, C_ARRAY, SSA and the device-resident index blob (host/src/serialization/csidx.hpp).

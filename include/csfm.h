@@ -164,6 +164,10 @@ CSFM_API int csfm_blob(const csfm_index* idx, const void** d_blob, uint64_t* byt
  * take_ownership == 0 the caller keeps the memory alive for the life of the handle. */
 CSFM_API int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownership,
                               csfm_index** out);
+/* A second handle over a copy of the blob on `device` (the same device, or a peer: the copy goes over
+ * NVLink when peer access can be enabled, else through the host). For single-process callers that want
+ * one replica per GPU without a communicator; the new handle owns its copy. */
+CSFM_API int csfm_replicate(const csfm_index* idx, int device, csfm_index** out);
 /* Host round trip of the same blob (checkpoint / .csidx device-layout section). */
 CSFM_API int csfm_blob_to_host(const csfm_index* idx, void* out, uint64_t bytes);
 CSFM_API int csfm_from_host_blob(const void* blob, uint64_t bytes, int device, csfm_index** out);

@@ -62,6 +62,7 @@ def test_cpp_batch_api(tmp_path):
     pkg = os.path.join(ROOT, "compressed-fm-index-implementation-with-learned-optimizations_b200")
     src.write_text(r'''
 #include "api/fm_index.hpp"
+#include "csfm.h"
 #include <cassert>
 #include <iostream>
 int main(int argc, char** argv) {
@@ -102,13 +103,30 @@ int main(int argc, char** argv) {
   auto loc2 = back.locate_batch(views, 17);
   assert(loc2.offsets == loc.offsets && loc2.positions == loc.positions && loc2.status == loc.status);
   assert(back.extract(4, 5) == text.substr(4, 5));
+  // replicas in one process: one per visible GPU (at least two handles, on the same device if there is only one)
+  int ndev = 0;
+  assert(csfm_device_count(&ndev) == 0 && ndev >= 1);
+  std::vector<cs::FMIndex> reps = {idx};
+  for (int d = 1; d < (ndev > 1 ? ndev : 2); ++d) reps.push_back(idx.replicate_to(d % ndev));
+  assert(reps[1].device() == 1 % ndev && reps[1].handle() != idx.handle());
+  std::vector<uint8_t> bytes;
+  std::vector<uint64_t> offs = {0};
+  std::vector<std::string> many;
+  for (int i = 0; i < 3001; ++i) many.push_back(text.substr((i * 37) % 4000, 1 + i % 9));
+  for (auto& s : many) { bytes.insert(bytes.end(), s.begin(), s.end()); offs.push_back(bytes.size()); }
+  std::vector<uint64_t> sharded(many.size()), single(many.size());
+  cs::FMIndex::count_batch_sharded(reps, bytes.data(), offs.data(), many.size(), sharded.data());
+  idx.count_batch(bytes.data(), offs.data(), many.size(), single.data());
+  assert(sharded == single);
+  cs::FMIndex big = cs::FMIndex::build_from_text(text, p, CSFM_BUILD_LARGE_TABLE);
+  assert(big.count_batch(pats) == counts);
   std::cout << "ok " << counts[0] << "\n";
   return 0;
 }
 ''')
     exe = tmp_path / "batch"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-std=c++20", "-O1", "-I" + os.path.join(pkg, "host", "src"), "-o", str(exe), str(src),
+    subprocess.run([cxx, "-std=c++20", "-O1", "-I" + os.path.join(pkg, "host", "src"), "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(src),
                     "-L" + os.path.join(pkg, "host"), "-lcs_b200", "-L" + pkg, "-lcsfm",
                     "-Wl,-rpath," + os.path.join(pkg, "host"), "-Wl,-rpath," + pkg], check=True)
     r = subprocess.run([str(exe), str(tmp_path)], capture_output=True, text=True, timeout=300)

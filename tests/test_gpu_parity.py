@@ -387,6 +387,100 @@ def test_async_submit32_compact(fm, force_text):
         assert (got.astype(np.uint64) == oc).all()
 
 
+def test_replicate_handle(fm):
+    """csfm_replicate: a second handle over its own copy of the blob (same device here; a peer device when the
+    box has one) answers like the original, also after the original is destroyed."""
+    import torch
+    rng = np.random.default_rng(9)
+    text, alpha = _rand_text(rng, 120_000, 70, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=4), flags=fm.BUILD_FORCE_TEXT_CHECK)
+    orc = oracle.OracleIndex(text, stride=4)
+    d, o = fm.pack_patterns(_mixed_patterns(rng, text, alpha, 5000, 24))
+    oc, ose = orc.count_batch(d, o)
+    ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=9)
+    reps = [idx.replicate(dev) for dev in range(min(2, torch.cuda.device_count()))] + [idx.replicate(0)]
+    assert all(r.info().blob_bytes == idx.info().blob_bytes for r in reps)
+    assert [r.info().device for r in reps][0] == 0 and reps[-1].blob()[0] != idx.blob()[0]
+    idx.close()
+    for r in reps:
+        assert (r.count_batch(d, o) == oc).all()
+        c, se = r.count_batch(d, o, want_intervals=True)
+        assert (c == oc).all() and (se == ose).all()
+        offs, pos, status = r.locate_batch(d, o, limit=9)
+        assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
+        r.close()
+
+
+def test_concurrent_host_threads_one_handle(fm):
+    """SURVEY §8b threading row: queries on ONE handle from several host threads (ctypes releases the GIL,
+    so the calls really overlap): host-pointer count and locate, device-pointer count on private streams and
+    the streaming form, all against the same oracle answers."""
+    import threading
+    import torch
+    rng = np.random.default_rng(5)
+    text, alpha = _rand_text(rng, 200_000, 40, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=8), flags=fm.BUILD_FORCE_TEXT_CHECK)
+    orc = oracle.OracleIndex(text, stride=8)
+    work = []
+    for k in range(6):
+        d, o = fm.pack_patterns(_mixed_patterns(rng, text, alpha, 4000 + 50 * k, 20))
+        oc, ose = orc.count_batch(d, o)
+        ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=7)
+        work.append((d, o, oc, ose, ooffs, opos, ostatus))
+    errors = []
+
+    def host_worker(k):
+        try:
+            d, o, oc, ose, ooffs, opos, ostatus = work[k]
+            for _ in range(6):
+                assert (idx.count_batch(d, o) == oc).all()
+                c, se = idx.count_batch(d, o, want_intervals=True)
+                assert (c == oc).all() and (se == ose).all()
+                offs, pos, status = idx.locate_batch(d, o, limit=7)
+                assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
+        except BaseException as e:  # noqa: BLE001 - reported by the main thread
+            errors.append(repr(e))
+
+    def device_worker(k):
+        try:
+            d, o, oc = work[k][:3]
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            db = torch.from_numpy(d).cuda()
+            do = torch.from_numpy(o.astype(np.int64)).cuda()
+            dc = torch.zeros(o.size - 1, dtype=torch.int64, device="cuda")
+            for _ in range(20):
+                dc.zero_()
+                stream.wait_stream(torch.cuda.current_stream())
+                idx.count_batch_device(db.data_ptr(), do.data_ptr(), o.size - 1, dc.data_ptr(), 0, stream.cuda_stream)
+                stream.synchronize()
+                assert (dc.cpu().numpy().astype(np.uint64) == oc).all()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def stream_worker(k):
+        try:
+            d, o, oc = work[k][:3]
+            hb = torch.from_numpy(d.copy()).pin_memory()
+            hl = torch.from_numpy(np.diff(o).astype(np.uint8)).pin_memory()
+            hc = torch.zeros(o.size - 1, dtype=torch.int32).pin_memory()
+            for _ in range(10):
+                hc.fill_(-1)
+                idx.count_batch_wait(idx.count_batch_submit_len8(hb.data_ptr(), int(o[-1]), hl.data_ptr(), o.size - 1, hc.data_ptr()))
+                assert (hc.numpy().view(np.uint32).astype(np.uint64) == oc).all()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=host_worker, args=(0,)), threading.Thread(target=host_worker, args=(1,)),
+               threading.Thread(target=device_worker, args=(2,)), threading.Thread(target=device_worker, args=(3,)),
+               threading.Thread(target=stream_worker, args=(4,)), threading.Thread(target=stream_worker, args=(5,))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 @pytest.mark.parametrize("force_text", [False, True])
 def test_async_submit_len8(fm, force_text):
     """csfm_count_batch_submit_len8: one length byte per pattern in (offsets rebuilt by a device prefix sum),
