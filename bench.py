@@ -44,7 +44,15 @@ WORKLOADS = {
                stride=32, desc="C3: 2^30 B text sigma=256, text-sampled patterns len 8..32, 1M-pattern batches"),
     "c2": dict(n_log2=26, kind="dna", seed_text=1, len_lo=20, len_hi=20, seed_len=0, seed_pos=2, batch=1_000_000,
                stride=32, desc="C2: 2^26 B DNA+$ text, text-sampled patterns len 20, 1M-pattern batches"),
+    # configs[4]: the index is BUILT on rank 0 (suffix array, BWT, levels: `construction`) and broadcast; the
+    # count sweep is steps x ranks 1M-pattern batches (100 steps on 1 GPU = the 100M patterns of the config)
+    "c5": dict(n=4_000_000_000, n_log2=32, kind="dna", seed_text=7, len_lo=20, len_hi=20, seed_len=0, seed_pos=11, batch=1_000_000,
+               stride=32, desc="C5: 4e9 B DNA+$ text built on the GPU, text-sampled patterns len 20, 1M-pattern batches"),
 }
+
+
+def text_size(args, wl):
+    return (1 << args.n_log2) if args.n_log2 else wl.get("n", 1 << wl["n_log2"])
 METRIC = "count queries/sec"
 NB = 8  # distinct resident batches cycled through the timed steps (8 x ~28 MB > L2 with the 1.15 GB index)
 
@@ -222,7 +230,7 @@ def run_reference(args, rank, world):
     import csfm_b200 as fm
     import oracle
     wl = dict(WORKLOADS[args.workload])
-    n = 1 << (args.n_log2 or wl["n_log2"])
+    n = text_size(args, wl)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     text = make_text(wl, n, dev)
@@ -460,7 +468,7 @@ def run_engine(args, rank, world, local_rank):
     import csfm_b200 as fm
 
     wl = dict(WORKLOADS[args.workload])
-    n = 1 << (args.n_log2 or wl["n_log2"])
+    n = text_size(args, wl)
     batch = args.batch or wl["batch"]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -490,6 +498,14 @@ def run_engine(args, rank, world, local_rank):
         idx, bcast_ms = fm.parallel.replicate_index(idx if rank == 0 else None, dev, src=0)  # the one ncclBroadcast
     info = idx.info()
     L = int(info.levels)
+    construction = None
+    if rank == 0:
+        construction = {"n": n, "seconds": build_s, "suffixes_per_s": n / build_s, "sa_rounds": int(info.sa_rounds),
+                        "sa_radix_passes": int(info.sa_radix_passes),
+                        "sort_bytes_moved_model": n * int(info.sa_radix_passes) * 2 * 12,
+                        "note": "csfm_build_from_text_device on device-resident text: suffix array (packed-key radix sort + prefix "
+                                "doubling), BWT, SSA, levels, k-mer and half-step tables, text sections; the model figure is n x "
+                                "8-bit radix passes x 2 x (8 B key + 4 B suffix)"}
     log(f"[rank {rank}] n={n} levels={L} sigma={info.sigma} blob={info.blob_bytes/1e6:.1f} MB text_gen={t_text:.2f}s "
         f"build={build_s if build_s is None else round(build_s, 2)}s bcast_ms={bcast_ms}")
 
@@ -815,7 +831,10 @@ def run_engine(args, rank, world, local_rank):
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, checked vs the GPU
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "c5":
+        cpu = {"value": None, "unit": "queries/s", "kind": "reference",
+               "sample": "not run at this size (the reference's index would have to be injected from a 4.3 GB plane set); see c2 / c3"}
+    elif world == 1 and not args.no_cpu_baseline:
         try:
             import oracle
             if not oracle.ref_available():
@@ -863,6 +882,7 @@ def run_engine(args, rank, world, local_rank):
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "construction": construction,
         "clocks": clocks.summary(),
         "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal, "compact_equals_u64_api": compact_equal},
         "locate": locate,

@@ -48,7 +48,8 @@ class IndexInfo(C.Structure):
     _fields_ = [("n", C.c_uint64), ("sigma", C.c_uint32), ("levels", C.c_uint32), ("ssa_stride", C.c_uint32),
                 ("device", C.c_uint32), ("nsamp", C.c_uint64), ("blocks_per_level", C.c_uint64),
                 ("blob_bytes", C.c_uint64), ("has_sa", C.c_uint32), ("layout", C.c_uint32), ("line_bytes", C.c_uint32),
-                ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("half_table", C.c_uint32)]
+                ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("half_table", C.c_uint32),
+                ("sa_rounds", C.c_uint32), ("sa_radix_passes", C.c_uint32)]
 
 
 class CallStats(C.Structure):

@@ -95,7 +95,8 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
   uint32_t *d_ssa = nullptr, *d_sa = nullptr;
   uint64_t nsamp = 0;
   const bool want_sa = (flags & CSFM_BUILD_KEEP_SA) || !((flags & CSFM_BUILD_NO_TEXT_CHECK) || (flags & CSFM_BUILD_LAYOUT_BINARY64));
-  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp, want_sa ? &d_sa : nullptr);
+  uint32_t sa_rounds = 0, sa_passes = 0;
+  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp, want_sa ? &d_sa : nullptr, &sa_rounds, &sa_passes);
   if (rc) return rc;
   rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, stride, device, flags, out, d_text, d_sa);
   cudaFree(d_bwt);
@@ -104,6 +105,8 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
     cudaFree(d_sa);
     return rc;
   }
+  (*out)->sa_rounds = sa_rounds;
+  (*out)->sa_radix_passes = sa_passes;
   if (flags & CSFM_BUILD_KEEP_SA)
     (*out)->d_sa = d_sa;
   else
@@ -212,6 +215,8 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->kmer_k = idx->view.kmer_k;
   out->text_check = idx->view.text != nullptr;
   out->half_table = idx->view.kmer_hi != nullptr;
+  out->sa_rounds = idx->sa_rounds;
+  out->sa_radix_passes = idx->sa_radix_passes;
   return CSFM_OK;
 }
 

@@ -51,6 +51,7 @@ struct csfm_index {
   csfm::BlobHeader h{};  // host copy of the header
   csfm::IndexView view{};
   uint32_t* d_sa = nullptr;  // CSFM_BUILD_KEEP_SA
+  uint32_t sa_rounds = 0, sa_radix_passes = 0;  // how the suffix sort of build_from_text went (0: index not built here)
 
   cudaStream_t stream = nullptr;  // used by the host-pointer API
   cudaStream_t aux_stream[2] = {nullptr, nullptr};  // slice pipeline of large host-pointer batches
@@ -89,7 +90,8 @@ int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: 
 // csfm_sa.cu
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,
-                        uint32_t** d_sa_out /*nullable: keep SA*/);
+                        uint32_t** d_sa_out /*nullable: keep SA*/, uint32_t* rounds_out = nullptr,
+                        uint32_t* passes_out = nullptr);
 // csfm_query.cu
 int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
                  uint64_t* d_counts, uint64_t* d_sp_ep, uint32_t* d_row_sp, uint32_t* d_row_cnt,

@@ -106,7 +106,9 @@ struct MaxOp {
 
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,
-                        uint32_t** d_sa_out) {
+                        uint32_t** d_sa_out, uint32_t* rounds_out, uint32_t* passes_out) {
+  if (rounds_out) *rounds_out = 0;
+  if (passes_out) *passes_out = 0;
   *d_bwt_out = nullptr;
   *d_ssa_out = nullptr;
   if (d_sa_out) *d_sa_out = nullptr;
@@ -181,6 +183,8 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
   for (int round = 0;; ++round) {
     size_t tb = tmp_bytes;
     SA_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tb, keys, vals, (int64_t)n, 0, end_bit, stream));
+    if (rounds_out) ++*rounds_out;
+    if (passes_out) *passes_out += (uint32_t)((end_bit + 7) / 8);  // 8-bit digits: each pass reads and writes every (key, suffix) pair
     SA_CUDA(cudaMemsetAsync(d_ngroups, 0, 8, stream));
     mark_heads_kernel<<<grid, block, 0, stream>>>(keys.Current(), n, heads, d_ngroups);
     unsigned long long ngroups = 0;

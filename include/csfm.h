@@ -107,6 +107,10 @@ typedef struct {
   uint32_t text_check; /* 1 = text + suffix array resident for the verification shortcut */
   uint32_t half_table; /* 1 = half-step table resident (two-level indexes: the first rank step of a
                           query needs only its second level) */
+  uint32_t sa_rounds;  /* build_from_text: sorting rounds of the suffix sort (1 = the packed first
+                          symbols already separated every suffix), 0 if the index was not built here */
+  uint32_t sa_radix_passes; /* 8-bit radix passes over the (u64 key, u32 suffix) pairs, all rounds:
+                               the sort moved about n * passes * 2 * 12 bytes */
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */
