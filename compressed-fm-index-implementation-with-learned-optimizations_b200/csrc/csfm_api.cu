@@ -192,6 +192,8 @@ void csfm_destroy(csfm_index* idx) {
   if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
   if (idx->ev0) cudaEventDestroy(idx->ev0);
   if (idx->ev1) cudaEventDestroy(idx->ev1);
+  for (auto& e : idx->ev_slice)
+    if (e) cudaEventDestroy(e);
   if (idx->stream) cudaStreamDestroy(idx->stream);
   for (auto& s : idx->aux_stream)
     if (s) cudaStreamDestroy(s);
@@ -624,7 +626,9 @@ int csfm_locate_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint
   if (rc) return rc;
   if (d_out_pos == nullptr && cap == 0) return CSFM_OK;  // sizing call
   if (cap < *total) return fail(CSFM_ERR_CAPACITY, "locate output buffer too small");
-  return locate_walk(idx, npat, d_out_offs, d_out_pos, *total, d_status, st);
+  rc = locate_expand(idx, npat, d_out_offs, d_out_pos, *total, st);
+  if (rc) return rc;
+  return locate_walk(idx, npat, d_out_offs, d_out_pos, 0, *total, d_status, st);
 }
 
 int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t limit,
@@ -671,9 +675,27 @@ int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* off
   if (tot) {
     rc = idx->ws_pos.ensure(tot * 8);
     if (rc) return rc;
-    rc = locate_walk(idx, npat, d_out_offs, idx->ws_pos.as<uint64_t>(), tot, d_status, st);
+    uint64_t* d_pos = idx->ws_pos.as<uint64_t>();
+    rc = locate_expand(idx, npat, d_out_offs, d_pos, tot, st);
     if (rc) return rc;
-    CSFM_CUDA(cudaMemcpyAsync(out_pos, idx->ws_pos.p, tot * 8, cudaMemcpyDeviceToHost, st));
+    // Large results leave in slices: the device->host copy of a slice (8 bytes per occurrence) runs on a
+    // second stream while the next slice is being walked.
+    const uint64_t nslices = (idx->instr_mask == 0 && tot >= (1ull << 22)) ? 4 : 1;
+    if (nslices > 1 && !idx->aux_stream[0]) CSFM_CUDA(cudaStreamCreateWithFlags(&idx->aux_stream[0], cudaStreamNonBlocking));
+    for (uint64_t s = 0; s < nslices; ++s) {
+      const uint64_t lo = tot * s / nslices, hi = tot * (s + 1) / nslices;
+      rc = locate_walk(idx, npat, d_out_offs, d_pos, lo, hi - lo, d_status, st);
+      if (rc) return rc;
+      cudaStream_t cs = st;
+      if (nslices > 1) {
+        if (!idx->ev_slice[s]) CSFM_CUDA(cudaEventCreateWithFlags(&idx->ev_slice[s], cudaEventDisableTiming));
+        CSFM_CUDA(cudaEventRecord(idx->ev_slice[s], st));
+        cs = idx->aux_stream[0];
+        CSFM_CUDA(cudaStreamWaitEvent(cs, idx->ev_slice[s], 0));
+      }
+      CSFM_CUDA(cudaMemcpyAsync(out_pos + lo, d_pos + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    if (nslices > 1) CSFM_CUDA(cudaStreamSynchronize(idx->aux_stream[0]));
   }
   if (status) CSFM_CUDA(cudaMemcpyAsync(status, d_status, npat * 4, cudaMemcpyDeviceToHost, st));
   CSFM_CUDA(cudaStreamSynchronize(st));

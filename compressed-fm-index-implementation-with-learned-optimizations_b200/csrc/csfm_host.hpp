@@ -62,6 +62,7 @@ struct csfm_index {
   } async_slot[CSFM_ASYNC_SLOTS];
   uint64_t next_ticket = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_slice[4] = {nullptr, nullptr, nullptr, nullptr};  // locate: walk slice done -> its copy may start
   csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
   unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators
   uint32_t counter_slot = 0;
@@ -99,8 +100,13 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
 int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
                 uint64_t limit, uint64_t* d_out_offs, int32_t* d_status, uint64_t* total,
                 cudaStream_t stream);
-int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos,
-                uint64_t total, int32_t* d_status, cudaStream_t stream);
+// rows of every output slot (uses the intervals locate_plan left in the workspace) ...
+int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
+                  cudaStream_t stream);
+// ... then rows -> text positions for the slots [first, first + count): LF walks, or one gather per row
+// when the index carries its whole suffix array
+int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t first,
+                uint64_t count, int32_t* d_status, cudaStream_t stream);
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream);
 // d_offs[0..count) = exclusive prefix sum of d_lens[0..count) (u8 lengths -> u64 offsets), on `stream`
 int offsets_from_lengths8(const uint8_t* d_lens, uint64_t count, uint64_t* d_offs, DeviceBuffer& scratch,

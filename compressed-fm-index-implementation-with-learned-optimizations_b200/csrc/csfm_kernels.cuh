@@ -221,6 +221,7 @@ struct CountArgs {
 
 struct WalkArgs {
   uint64_t* out_pos;  // in: SA row, out: text position
+  unsigned long long first;  // this launch walks the output slots [first, first + total)
   unsigned long long total;
   const uint64_t* out_offs;  // npat+1 (to attribute a failed walk to its query)
   unsigned long long npat;

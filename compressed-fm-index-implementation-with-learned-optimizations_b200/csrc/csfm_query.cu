@@ -206,7 +206,7 @@ walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkAr
   for (;;) {
     const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
     if (item != ~0ull) {
-      slot = item;
+      slot = a.first + item;
       start = (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
@@ -414,25 +414,34 @@ __global__ void rows_to_positions_kernel(const uint32_t* __restrict__ sa, uint64
     out_pos[i] = sa[(uint32_t)out_pos[i]];
 }
 
-int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
-                int32_t* d_status, cudaStream_t stream) {
+int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
+                  cudaStream_t stream) {
   if (npat == 0 || total == 0) return CSFM_OK;
   const uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
   expand_rows_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(d_row_sp, d_out_offs, npat, d_out_pos);
+  CSFM_CUDA(cudaGetLastError());
+  idx->stats.kernel_launches += 1;
+  return CSFM_OK;
+}
+
+int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t first,
+                uint64_t count, int32_t* d_status, cudaStream_t stream) {
+  if (npat == 0 || count == 0) return CSFM_OK;
   if (idx->view.dense && idx->view.dense_shift == 0 && !idx->no_sa_locate) {
     const bool timed_sa = (idx->instr_mask & 2u) != 0;
     if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-    rows_to_positions_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(idx->view.dense, d_out_pos, total);
+    rows_to_positions_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(idx->view.dense, d_out_pos + first, count);
     if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
     CSFM_CUDA(cudaGetLastError());
-    idx->stats.kernel_launches += 2;
+    idx->stats.kernel_launches += 1;
     return CSFM_OK;
   }
   unsigned long long* ctr = next_counter_slot(idx);
   CSFM_CUDA(cudaMemsetAsync(ctr, 0, kCounterWords * sizeof(unsigned long long), stream));
   WalkArgs w{};
   w.out_pos = d_out_pos;
-  w.total = total;
+  w.first = first;
+  w.total = count;
   w.out_offs = d_out_offs;
   w.npat = npat;
   w.status = d_status;
@@ -440,7 +449,7 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   w.lf_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
   const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
-  const uint64_t want = (total * 4 + kThreads - 1) / kThreads;
+  const uint64_t want = (count * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
@@ -450,7 +459,7 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
     walk_kernel<<<grid, kThreads, 0, stream>>>(idx->view, w);
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
   CSFM_CUDA(cudaGetLastError());
-  idx->stats.kernel_launches += 2;
+  idx->stats.kernel_launches += 1;
   if (w.lf_total)
     CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 9, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
   return CSFM_OK;

@@ -689,7 +689,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
   for (;;) {
     const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
     if (item != ~0ull) {
-      slot = item;
+      slot = a.first + item;
       start = (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
