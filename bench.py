@@ -438,7 +438,7 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
     # ---- an index that keeps its whole suffix array (4 n bytes more): a row's position is one gather
     try:
         idx_sa = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=dev.index,
-                                                   flags=fm.BUILD_FORCE_TEXT_CHECK)
+                                                   flags=fm.BUILD_FORCE_TEXT_CHECK | fm.BUILD_KEEP_SA)
         d_pos2 = torch.zeros_like(d_pos)
         ms_sa = timed(lambda: run(idx_sa, d_pos2), iters, all_ranks=False)  # rank 0 only
         out["resident_sa"] = {"value": total / (ms_sa / 1e3), "unit": "occurrences/s", "ms_per_batch": ms_sa, "n_gpus": 1,
@@ -446,6 +446,30 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
                               "positions_equal_walk": bool(torch.equal(d_pos, d_pos2)),
                               "note": "CSFM_BUILD_FORCE_TEXT_CHECK: text + full suffix array ride in the index blob, locate "
                                       "reads SA[row] instead of walking LF to a sampled row (same positions, same order)"}
+        # walk-length histogram of the batch, from the resident suffix array: the walk of an
+        # occurrence at text position p ends at the nearest sampled position at or before p (cyclically), so
+        # its length is the distance to it. The sum must equal the LF steps the walk kernel counted.
+        try:
+            sa = torch.as_tensor(_DevMem(idx_sa.sa_device_ptr(), 4 * n), device=dev).view(torch.int32)  # n < 2^31 here
+            sampled = sa[::32].to(torch.int64)                 # SA[k * stride]: the positions whose rows are sampled
+            mark = torch.full((n,), -1, dtype=torch.int64, device=dev)
+            mark[sampled] = sampled
+            prev = torch.cummax(mark, 0).values               # nearest sampled position <= q, -1 if none
+            del mark
+            pp = prev[d_pos]
+            wl = torch.where(pp >= 0, d_pos - pp, d_pos + (n - int(sampled.max())))
+            del prev, pp
+            edges = [0, 1, 8, 16, 32, 64, 128, 256]
+            hist = torch.bincount(torch.bucketize(wl, torch.tensor(edges[1:], device=dev), right=True), minlength=len(edges))
+            out["walk_lengths"] = {"mean": float(wl.double().mean()), "max": int(wl.max()),
+                                   "p50": int(wl.kthvalue(max(1, wl.numel() // 2)).values),
+                                   "p99": int(wl.kthvalue(max(1, int(wl.numel() * 0.99))).values),
+                                   "bucket_edges": edges, "bucket_counts": [int(x) for x in hist.cpu()],
+                                   "sum_equals_lf_steps_counted": int(wl.sum()) == lf_steps,
+                                   "note": "LF steps per occurrence of this rank's batch; buckets are [edge_i, edge_i+1), the last one open"}
+            del wl
+        except Exception as e:  # pragma: no cover
+            out["walk_lengths"] = {"unavailable": repr(e)}
         idx_sa.close()
         del d_pos2
     except Exception as e:  # pragma: no cover
