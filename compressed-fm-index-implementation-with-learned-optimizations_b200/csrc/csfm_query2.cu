@@ -14,6 +14,13 @@
 // same line after ~4 steps: then one load and one hit word serve both ends, and the warp skips
 // the second hit computation altogether when no sub-warp needs it. Grids are persistent.
 //
+// A query does not start at its last character: the k-mer jump table gives the interval of its last
+// k characters in one lookup; on two-level indexes the half-step table gives that interval already
+// mapped through level 0 for the next character's high nibble, so the first rank step reads only its
+// level-1 line. When the index carries the text and the suffix array, a query whose interval is down
+// to at most four rows finishes by comparing its remaining characters with the text in front of those
+// suffixes (count2_kernel<true,.>); with a large table the lookup itself may leave so few rows.
+//
 // Replaces cs::FMIndex::count / locate (/root/reference/src/api/fm_index.cpp:79-157),
 // cs::WaveletTree::rank / access (src/core/wavelet.cpp:59-128) and cs::BitVector::rank1
 // (src/core/bitvector.cpp:165-230).
@@ -184,27 +191,27 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
             pre = true;
           }
         } else {
-        if (present) se = iv.kmer[e];
-        sp = se.x;
-        ep = se.y;
-        if (sp >= ep) {
-          finish(0, 0, 0);
-        } else if (m == kk) {
-          finish(ep - sp, sp, ep);
-        } else {
-          rem = (uint32_t)(m - kk);
-          ptr = a.bytes + (o1 - kk);  // the last character the lookup consumed
-          if (shortcut && ep - sp <= max_rows && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
-            // a long table key already leaves few rows: verify them without a rank step
-            next_byte = ptr[-1];
-            if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
-            vstage = 1;
-            if (kInstr) ++my_checks;
+          if (present) se = iv.kmer[e];
+          sp = se.x;
+          ep = se.y;
+          if (sp >= ep) {
+            finish(0, 0, 0);
+          } else if (m == kk) {
+            finish(ep - sp, sp, ep);
           } else {
-            --ptr;
-            begin_step(*ptr);
+            rem = (uint32_t)(m - kk);
+            ptr = a.bytes + (o1 - kk);  // the last character the lookup consumed
+            if (shortcut && ep - sp <= max_rows && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
+              // a long table key already leaves few rows: verify them without a rank step
+              next_byte = ptr[-1];
+              if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
+              vstage = 1;
+              if (kInstr) ++my_checks;
+            } else {
+              --ptr;
+              begin_step(*ptr);
+            }
           }
-        }
         }
       } else {
         // first step needs no rank: occ(c,0) = 0 and occ(c,n) = freq[c]  => [C[c], C[c+1])
