@@ -903,7 +903,8 @@ def run_engine(args, rank, world, local_rank):
                             "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
                             "api": "csfm_count_batch_submit/_wait (u64 offsets and counts)"},
                 "sync_call_ms_per_step": e2e_sync_ms, "sync_call_value": world * batch / (e2e_sync_ms / 1e3)},
-        "gpu_launches": launches,
+        "gpu_launches": args.steps,  # the timed region of `value`: one count kernel per step
+        "gpu_launches_all_timed_legs": launches + e2e_steps * (1 + 3 + 4),  # + stepping-only, large-table, e2e forms (u64 1, u32 3, len8 4 kernels per step)
         "roofline": roofline,
         "cpu_baseline": cpu,
         "construction": construction,
