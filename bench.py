@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the FM-index count() hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5] [--large-table] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (default c3 = BASELINE.json configs[2], the configuration the metric's target is quoted
-on): 2^30-byte synthetic text over bytes 1..255 + 0x00 terminator (sigma = 256, 8 wavelet levels),
-text-sampled patterns of length 8..32, processed in 1 M-pattern batches. A "step" is one pass of
-count_batch over one 1 M-pattern batch per GPU (weak scaling: every rank runs its own batches
-against its own replica of the index; the index is built once on rank 0 and replicated with one
-NCCL broadcast of the device blob).
+on): 2^30-byte synthetic text over bytes 1..255 + 0x00 terminator (sigma = 256, 8 wavelet levels in
+the reference), text-sampled patterns of length 8..32, processed in 1 M-pattern batches. A "step" is
+one pass of count_batch over one 1 M-pattern batch per GPU (weak scaling: every rank runs its own
+batches against its own replica of the index; the index is built once on rank 0 and replicated with
+one NCCL broadcast of the device blob).
 
 One JSON line on stdout (rank 0):
   value      whole-job count queries/s with the batches already resident in HBM (CUDA events)
-  e2e        the same through the host-pointer C ABI (csfm_count_batch): pinned host buffers,
-             H2D of patterns+offsets and D2H of the counts inside the timed region
-  roofline   algorithmic bytes (executed backward-search steps x 2 x L x line bytes) over
-             the mean kernel duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  e2e        the same through the streaming host-pointer C ABI (csfm_count_batch_submit_len8/_wait):
+             pinned host buffers, H2D of lengths + patterns and D2H of the counts inside the timed
+             region, three steps in flight; the u32-offset, u64-offset and synchronous forms beside it
+  roofline   executed algorithmic bytes (rank steps x 2 x L x line, half steps, table lookups, text
+             verifications) over the mean kernel duration, against the measured HBM copy
+             peak (MEASURED_PEAKS.json); `traffic` from the committed ncu capture; the stepping-only
+             kernel and the large-table index on the same batches as sub-objects
   cpu_baseline  the UNMODIFIED reference cs::FMIndex::count (oracle/_ref/libcsref.so) on all host
              cores over a bounded sample of the same batch, checked bit-exact against the GPU
+  construction  build of the main index: seconds, suffixes/s, sorting rounds, radix passes
+  locate     configs[3]: occurrences/s of locate_batch on every rank (weak), with its own roofline,
+             host-pointer e2e, resident-SA variant, walk-length histogram and reference baseline
 
 --impl reference times only that CPU reference (rank 0; other ranks exit 0).
 """
