@@ -631,7 +631,7 @@ def run_engine(args, rank, world, local_rank):
         del d_spep
 
     # ---- the same batches on an index built with a LARGE k-mer table budget (opt-in, CSFM_BUILD_LARGE_TABLE):
-    # for a byte alphabet k goes from 3 to 4 (2^32 entries, 34 GB), the lookup leaves ~1 row and the query
+    # for a byte alphabet k goes from 3 to 4 (2^32 entries, 17 GB), the lookup leaves ~1 row and the query
     # goes straight to the text verification: one table line + one suffix-array line + one text line
     large = None
     if world == 1 and not args.no_large_table and not args.large_table and int(info.layout) == 2 and torch.cuda.mem_get_info()[0] > 100e9:

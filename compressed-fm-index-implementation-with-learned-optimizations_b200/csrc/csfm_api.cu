@@ -308,10 +308,11 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   if (h.kmer_k) {
     uint64_t entries = 1;
     for (uint32_t i = 0; i < h.kmer_k && entries <= (1ull << 40); ++i) entries *= h.kmer_radix;
+    const uint64_t table_bytes = h.kmer_tiled ? (entries + 1) * 4 : entries * 8;
     if (!nib || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
-        h.off_kmer + entries * 8 > h.total_bytes)
+        h.kmer_tiled > 1 || (h.kmer_tiled && !h.off_text) || h.off_kmer + table_bytes > h.total_bytes)
       return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
-    if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + entries * 8 || h.off_kmer_hi + entries * 128 > h.total_bytes))
+    if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + table_bytes || h.off_kmer_hi + entries * 128 > h.total_bytes))
       return fail(CSFM_ERR_FORMAT, "inconsistent half-step table in blob header");
   }
   auto* idx = new (std::nothrow) csfm_index();

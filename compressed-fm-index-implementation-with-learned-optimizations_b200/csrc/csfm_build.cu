@@ -324,6 +324,7 @@ int index_finish_handle(csfm_index* idx) {
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
+  v.kmer_tiled = h.kmer_tiled;
   v.kmer_hi = (h.kmer_k && h.off_kmer_hi) ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer_hi) : nullptr;
   if (std::getenv("CSFM_NO_HALF_TABLE")) v.kmer_hi = nullptr;  // experiment knob: ignore a table that is present
   v.text = h.off_text ? idx->d_blob + h.off_text : nullptr;
@@ -393,7 +394,25 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // k-mer jump table: the first k steps of a query become one lookup. Budget: a quarter of the
   // level bytes, between 1 MiB and 1 GiB (k = 3 for a byte alphabet at n = 2^30, 9 for DNA+$ at 2^26,
   // 11 for DNA+$ at 4e9).
+  // (decided first because it also selects the table format) Text sections: see below.
+  const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
+  if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
+  if (flags & CSFM_BUILD_LARGE_TABLE) {
+    // after a long key little is left to step through: verify from three characters on, whatever the level count
+    flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
+    h.verify_min = 3;
+  }
+  bool text_sections = false;
+  if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
+      ((levels_in_hbm && L == 2) || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
+    uint8_t last = 0;
+    const cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
+    text_sections = e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0;
+  }
   if (nib && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
+    // with the text on board the table holds sp only (4 bytes per key) and is filled from the text's k-gram histogram
+    const bool tiled = text_sections && !std::getenv("CSFM_BUILD_PAIR_TABLE");
+    const uint64_t entry_bytes = tiled ? 4 : 8;
     const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : h.sigma;
     uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
     if (flags & CSFM_BUILD_LARGE_TABLE) {
@@ -408,15 +427,17 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
     uint32_t k = 0;
     uint64_t entries = 1;
     // a key that already leaves a quarter of a row on average gains nothing from another character
-    while (radix >= 2 && entries * radix * 8 <= budget && k < 16 && entries < 4 * n) {
+    // (the kernels build keys in 32 bits: at most 2^32 of them)
+    while (radix >= 2 && entries * radix * entry_bytes <= budget && entries * radix <= (1ull << 32) && k < 16 && entries < 4 * n) {
       entries *= radix;
       ++k;
     }
     if (k >= 2) {
       h.kmer_k = k;
       h.kmer_radix = (uint32_t)radix;
+      h.kmer_tiled = tiled ? 1u : 0u;
       h.off_kmer = h.total_bytes;
-      h.total_bytes = align_up(h.off_kmer + entries * 8, 256);
+      h.total_bytes = align_up(h.off_kmer + (tiled ? (entries + 1) * 4 : entries * 8), 256);
       // half-step table: 16 entries per k-mer; kept when it is no larger than the levels themselves
       // (C3: k = 3, 2.1 GB beside 2.3 GB of levels) and the table is not already a large one
       const uint64_t hi_bytes = entries * 16 * 8;
@@ -436,23 +457,11 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // On a one-level index (sigma <= 16) a step is a single fetch and the plain kernel (32 registers,
   // full occupancy) wins unless patterns are long: measured on the 4e9-byte DNA text, 2.68e9 q/s
   // plain vs 2.37e9 with the verification variant that never fires. So: two levels, in HBM.
-  const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
-  if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
-  if (flags & CSFM_BUILD_LARGE_TABLE) {
-    // after a long key little is left to step through: verify from three characters on, whatever the level count
-    flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
-    h.verify_min = 3;
-  }
-  if (nib && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_NO_TEXT_CHECK) &&
-      ((levels_in_hbm && L == 2) || (flags & CSFM_BUILD_FORCE_TEXT_CHECK))) {
-    uint8_t last = 0;
-    cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
-    if (e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0) {
-      h.dense_shift = 0;  // the full suffix array: no extra steps to reach a sampled row
-      h.off_text = h.total_bytes;
-      h.off_dense = align_up(h.off_text + n + 64, 256);
-      h.total_bytes = align_up(h.off_dense + (((n - 1) >> h.dense_shift) + 1) * 4, 256);
-    }
+  if (text_sections) {
+    h.dense_shift = 0;  // the full suffix array: no extra steps to reach a sampled row
+    h.off_text = h.total_bytes;
+    h.off_dense = align_up(h.off_text + n + 64, 256);
+    h.total_bytes = align_up(h.off_dense + (((n - 1) >> h.dense_shift) + 1) * 4, 256);
   }
 
   idx->blob_bytes = h.total_bytes;

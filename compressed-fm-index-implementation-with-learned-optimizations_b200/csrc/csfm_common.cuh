@@ -72,7 +72,7 @@ struct BlobHeader {
   // code e % radix, the one before it (e / radix) % radix, ...; (0,0) when it does not occur.
   uint32_t kmer_k;             // 0 = no table
   uint32_t kmer_radix;         // number of compact codes (sigma, or 256 with NO_COMPACT)
-  uint64_t off_kmer;           // byte offset of the table (uint2 entries)
+  uint64_t off_kmer;           // byte offset of the table (uint2 entries, or u32 when kmer_tiled)
   // text-verification shortcut (layout 2, texts with a unique smallest last byte): the text and
   // SA[k << dense_shift] for every k, so that a query whose interval has shrunk to ONE row can
   // finish by comparing its remaining characters with the text instead of stepping through them.
@@ -85,7 +85,11 @@ struct BlobHeader {
   // at entry e * 16 + g. A query with more than k characters starts from it and needs only the
   // level-1 half of its first rank step. 0 = absent.
   uint64_t off_kmer_hi;
-  uint32_t reserved0[2];
+  // 1: the k-mer table holds sp only, entries + 1 u32 values, ep(e) = sp(e + 1). Used when the text
+  // ends in a unique smallest byte: rows are then sorted rotations, the intervals of all k-mers tile
+  // [0, n) in key order, and the table is the prefix sum of the text's (cyclic) k-gram histogram.
+  uint32_t kmer_tiled;
+  uint32_t reserved0[1];
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
@@ -111,6 +115,8 @@ struct IndexView {
   const uint32_t* dense;  // SA[k << dense_shift]
   uint32_t kmer_k;
   uint32_t kmer_radix;
+  uint32_t kmer_tiled;  // table format, see BlobHeader
+  uint32_t pad0;
   uint64_t level_stride;
   uint32_t n;
   uint32_t L;

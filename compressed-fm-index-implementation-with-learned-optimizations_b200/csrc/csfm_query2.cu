@@ -26,6 +26,8 @@
 // (src/core/bitvector.cpp:165-230).
 #include <algorithm>
 
+#include <cub/device/device_scan.cuh>
+
 #include "csfm_host.hpp"
 #include "csfm_kernels.cuh"
 
@@ -191,7 +193,14 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
             pre = true;
           }
         } else {
-          if (present) se = iv.kmer[e];
+          if (present) {
+            if (iv.kmer_tiled) {  // sp only: the next key's sp is this key's ep
+              const uint32_t* const t = reinterpret_cast<const uint32_t*>(iv.kmer);
+              se = make_uint2(t[e], t[(size_t)e + 1]);
+            } else {
+              se = iv.kmer[e];
+            }
+          }
           sp = se.x;
           ep = se.y;
           if (sp >= ep) {
@@ -371,12 +380,33 @@ kmer_build_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tabl
   }
 }
 
+// Tiled table, step 1: histogram of the text's cyclic k-grams. Key of the k-gram starting at p: its LAST
+// character is the least significant digit (the order count2_kernel builds its key in), so keys sort like
+// the k-grams themselves and the exclusive prefix sum of the histogram is sp of every key.
+__global__ void __launch_bounds__(kThreads)
+kmer_histogram_kernel(const uint8_t* __restrict__ text, unsigned long long n, uint32_t k, uint32_t radix,
+                      const BlobHeader* __restrict__ hdr, uint32_t* __restrict__ table) {
+  __shared__ uint8_t code_of_byte[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) code_of_byte[i] = hdr->code_of_byte[i];
+  __syncthreads();
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+    unsigned long long e = 0;
+    for (uint32_t i = 0; i < k; ++i) {  // first character first: e = e * radix + code
+      unsigned long long q = p + i;
+      if (q >= n) q -= n;  // rows are rotations: the k-gram wraps around the text end
+      e = e * radix + code_of_byte[text[q]];
+    }
+    atomicAdd(&table[e], 1u);
+  }
+}
+
 // Fills the half-step table from the finished k-mer table: entry e * 16 + g = the interval of k-mer e
 // mapped through level 0 for the high nibble g. The two lines of an interval are loaded once and
 // serve all 16 nibbles.
 __global__ void __launch_bounds__(kThreads)
 kmer_hi_build_kernel(const __grid_constant__ IndexView iv, const uint2* __restrict__ table, uint2* __restrict__ table_hi,
-                     unsigned long long entries) {
+                     unsigned long long entries, bool tiled) {
   __shared__ Tables tb;
   load_tables(tb, iv.hdr);
   const int j = threadIdx.x & 3;
@@ -387,7 +417,8 @@ kmer_hi_build_kernel(const __grid_constant__ IndexView iv, const uint2* __restri
   for (unsigned long long t = 0; t < trips; ++t) {
     const unsigned long long e = t * ngroups + group;
     const bool valid = e < entries;
-    const uint2 se = valid ? table[e] : make_uint2(0u, 0u);
+    uint2 se = make_uint2(0u, 0u);
+    if (valid) se = tiled ? make_uint2(reinterpret_cast<const uint32_t*>(table)[e], reinterpret_cast<const uint32_t*>(table)[e + 1]) : table[e];
     const bool alive = valid && se.x < se.y;
     const uint32_t ls = se.x & ~(kSymsPerLine - 1), le = se.y & ~(kSymsPerLine - 1);
     Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
@@ -802,12 +833,32 @@ int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
   v.kmer = nullptr;
   v.kmer_hi = nullptr;
   v.kmer_k = 0;
-  kmer_build_kernel<<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
-  CSFM_CUDA(cudaGetLastError());
+  if (h.kmer_tiled) {
+    // histogram of the text's k-grams (the text copy inside the blob), then an in-place exclusive prefix sum
+    // over entries + 1 counters: table[e] = sp(e), table[entries] = n
+    if (!h.off_text) return fail(CSFM_ERR_FORMAT, "tiled k-mer table without text section");
+    uint32_t* t32 = reinterpret_cast<uint32_t*>(table);
+    CSFM_CUDA(cudaMemsetAsync(t32, 0, (entries + 1) * 4, stream));
+    kmer_histogram_kernel<<<idx->num_sms * 8, kThreads, 0, stream>>>(idx->d_blob + h.off_text, h.n, h.kmer_k, h.kmer_radix,
+                                                                  v.hdr, t32);
+    CSFM_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CSFM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, t32, t32, (int64_t)(entries + 1), stream));
+    void* d_tmp = nullptr;
+    CSFM_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 16));
+    const cudaError_t se = cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, t32, t32, (int64_t)(entries + 1), stream);
+    const cudaError_t sy = cudaStreamSynchronize(stream);
+    cudaFree(d_tmp);
+    CSFM_CUDA(se);
+    CSFM_CUDA(sy);
+  } else {
+    kmer_build_kernel<<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
+    CSFM_CUDA(cudaGetLastError());
+  }
   if (h.off_kmer_hi) {
     uint2* table_hi = reinterpret_cast<uint2*>(idx->d_blob + h.off_kmer_hi);
     const int grid_hi = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm((const void*)kmer_hi_build_kernel));
-    kmer_hi_build_kernel<<<grid_hi, kThreads, 0, stream>>>(v, table, table_hi, entries);
+    kmer_hi_build_kernel<<<grid_hi, kThreads, 0, stream>>>(v, table, table_hi, entries, h.kmer_tiled != 0);
     CSFM_CUDA(cudaGetLastError());
   }
   CSFM_CUDA(cudaStreamSynchronize(stream));

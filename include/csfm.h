@@ -86,7 +86,7 @@ typedef struct {
                                       at most 1 GiB. The lookup then leaves only a few rows and the query goes
                                       straight to the text verification (implies CSFM_BUILD_FORCE_TEXT_CHECK):
                                       three dependent fetches per query. Same results, 1.5-1.9x the count
-                                      throughput, an index of 10-40 GB */
+                                      throughput, an index of 10-25 GB */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
 
