@@ -121,7 +121,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.002)  # the timed region of `value` lasts ~30 ms: sample it densely
 
     def __enter__(self):
         if self._h is not None:
