@@ -107,3 +107,46 @@ def test_batch_threads_equal_single():
         k = int(offs[q + 1] - offs[q])
         assert rn[q] == k
         assert (rpos[q * 50:q * 50 + k] == pos[int(offs[q]):int(offs[q + 1])]).all()
+
+
+# ---- property test: arbitrary small texts, with and without a terminator ------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+_texts = st.one_of(
+    st.binary(min_size=1, max_size=200),
+    st.lists(st.sampled_from(list(b"ACGT")), min_size=1, max_size=300).map(bytes),
+    st.lists(st.sampled_from([0, 1, 255]), min_size=1, max_size=120).map(bytes),
+    st.builds(lambda unit, reps, tail: unit * reps + tail, st.binary(min_size=1, max_size=4), st.integers(1, 60),
+              st.binary(max_size=3)),
+)
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(text=_texts, stride=st.sampled_from([1, 2, 3, 4, 7, 32]), limit=st.sampled_from([1, 2, 5, 100000]),
+       seed=st.integers(0, 2**31 - 1), terminate=st.booleans())
+def test_oracle_equals_reference_on_arbitrary_texts(text, stride, limit, seed, terminate):
+    """The restatement against the compiled reference where the reference's behaviour is odd but
+    deterministic (SURVEY §8a notes 3-6): cyclic over-count without a terminator, LF walks that never
+    reach a sampled row (the reference throws -> status 1), byte 0x00 as an ordinary symbol."""
+    if terminate:
+        text = text + b"\x00"
+    R = oracle.RefIndex(text, stride=stride)
+    O = oracle.OracleIndex(text, stride=stride)
+    assert (R.sa == O.sa).all() and (R.bwt == O.bwt).all() and (R.C == O.C).all() and (R.ssa == O.ssa).all()
+    rng = np.random.default_rng(seed)
+    t = np.frombuffer(text, np.uint8)
+    pats = [b"", text[-min(len(text), 30):], text[:1]]
+    for _ in range(25):
+        m = int(rng.integers(1, 9))
+        if rng.random() < 0.7 and t.size > m:
+            s = int(rng.integers(0, t.size - m + 1))
+            pats.append(t[s:s + m].tobytes())
+        else:
+            pats.append(rng.integers(0, 256, m, dtype=np.uint8).tobytes())
+    for pat in pats:
+        assert O.count(pat) == R.count(pat)
+        opos, ost = O.locate(pat, limit)
+        rpos, rst = R.locate(pat, limit)
+        assert ost == rst
+        if rst == 0:
+            assert opos == rpos
