@@ -88,6 +88,7 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
   int rc = check_device(device);
   if (rc) return rc;
   if (n && !d_text) return fail(CSFM_ERR_INVALID, "text is null");
+  if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
   DeviceGuard g(device);
   if (!g.ok) return fail(CSFM_ERR_CUDA, "cudaSetDevice failed");
   const uint32_t stride = stride_of(params);
@@ -192,6 +193,7 @@ void csfm_destroy(csfm_index* idx) {
   if (idx->h_pinned) cudaFreeHost(idx->h_pinned);
   if (idx->ev0) cudaEventDestroy(idx->ev0);
   if (idx->ev1) cudaEventDestroy(idx->ev1);
+  if (idx->ev_ws_tmp) cudaEventDestroy(idx->ev_ws_tmp);
   for (auto& e : idx->ev_slice)
     if (e) cudaEventDestroy(e);
   if (idx->stream) cudaStreamDestroy(idx->stream);
@@ -314,6 +316,38 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
       return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
     if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + table_bytes || h.off_kmer_hi + entries * 128 > h.total_bytes))
       return fail(CSFM_ERR_FORMAT, "inconsistent half-step table in blob header");
+  }
+  // The kernels turn header tables into line addresses without further checks: a corrupt or crafted
+  // .csidx must fail here, not as an illegal address inside a kernel (which poisons the context).
+  {
+    if (h.n > kMaxN || h.sigma > 256 || h.code_bits > 8 || h.total_bytes < kHeaderBytes)
+      return fail(CSFM_ERR_FORMAT, "blob header: n / sigma / code_bits out of range");
+    const uint64_t lines_end = h.off_levels + (uint64_t)h.levels * h.level_stride;
+    if (h.level_stride > h.total_bytes || lines_end > h.total_bytes || h.nsamp > h.total_bytes / 4)
+      return fail(CSFM_ERR_FORMAT, "blob header: section sizes overflow the blob");
+    if (h.C[0] != 0 || h.C[256] != h.n) return fail(CSFM_ERR_FORMAT, "blob header: C array does not span [0, n]");
+    uint32_t present = 0;
+    for (int c = 0; c < 256; ++c) {
+      if (h.C[c + 1] < h.C[c]) return fail(CSFM_ERR_FORMAT, "blob header: C array not monotone");
+      if (h.C[c + 1] != h.C[c]) {
+        ++present;
+        if (nib && (h.code_of_byte[c] >> 4) >= (h.levels == 2 ? 16u : 1u))
+          return fail(CSFM_ERR_FORMAT, "blob header: compact code does not fit the level count");
+        if (!nib && h.levels < 8 && (h.code_of_byte[c] >> h.levels) != 0)
+          return fail(CSFM_ERR_FORMAT, "blob header: compact code does not fit the level count");
+      }
+    }
+    if (present != h.sigma) return fail(CSFM_ERR_FORMAT, "blob header: sigma differs from the C array");
+    for (int g = 0; g < 16; ++g)
+      if (h.start1[g] > h.n || (g && h.start1[g] < h.start1[g - 1]))
+        return fail(CSFM_ERR_FORMAT, "blob header: start1 not monotone within [0, n]");
+    if (!nib)
+      for (uint32_t l = 0; l < h.levels; ++l)
+        if (h.zeros[l] > h.n) return fail(CSFM_ERR_FORMAT, "blob header: zeros[] beyond n");
+    if (h.kmer_k && h.kmer_radix != h.sigma && h.kmer_radix != 256)
+      return fail(CSFM_ERR_FORMAT, "blob header: k-mer radix differs from the alphabet");
+    if (h.off_text && h.dense_shift != 0) return fail(CSFM_ERR_FORMAT, "blob header: text sections need the full suffix array");
+    if (h.verify_min > 64) return fail(CSFM_ERR_FORMAT, "blob header: verify_min out of range");
   }
   auto* idx = new (std::nothrow) csfm_index();
   if (!idx) return fail(CSFM_ERR_NOMEM, "host allocation failed");

@@ -62,6 +62,9 @@ struct csfm_index {
   } async_slot[CSFM_ASYNC_SLOTS];
   uint64_t next_ticket = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_ws_tmp = nullptr;  // locate: recorded after the last reader of ws_tmp (expand_rows)
+  bool ws_tmp_busy = false;
+  uint32_t total_slot = 0;  // locate: rotating pinned slot the total is read back into
   cudaEvent_t ev_slice[4] = {nullptr, nullptr, nullptr, nullptr};  // locate: walk slice done -> its copy may start
   csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
   unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators

@@ -371,34 +371,34 @@ int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs,
     CSFM_CUDA(cudaStreamSynchronize(stream));
     return CSFM_OK;
   }
-  int rc = idx->ws_tmp.ensure(npat * 8 + 256);
+  // a device-pointer caller may run locate on several streams: the previous call's expand kernel must be done
+  // with the intervals in ws_tmp before this call overwrites them
+  if (idx->ws_tmp_busy) CSFM_CUDA(cudaStreamWaitEvent(stream, idx->ev_ws_tmp, 0));
+  int rc = idx->ws_tmp.ensure((npat + 1) * 8 + 256);
   if (rc) return rc;
   uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
-  uint32_t* d_row_cnt = d_row_sp + npat;
+  uint32_t* d_row_cnt = d_row_sp + (npat + 1);
   const uint32_t saved_mask = idx->instr_mask;
   idx->instr_mask &= ~3u;  // in locate the instrumentation belongs to the walk kernel
   rc = count_device(idx, d_bytes, d_offs, npat, nullptr, nullptr, d_row_sp, d_row_cnt, limit, stream);
   idx->instr_mask = saved_mask;
   if (rc) return rc;
+  // npat + 1 items with a zero tail: out_offs[npat] = the total comes out of the same scan, on the device
+  CSFM_CUDA(cudaMemsetAsync(d_row_cnt + npat, 0, 4, stream));
   // u32 inputs accumulated into u64 outputs (the init value's type drives the accumulator)
   size_t tmp_bytes = 0;
   CSFM_CUDA(cub::DeviceScan::ExclusiveScan(nullptr, tmp_bytes, d_row_cnt, d_out_offs, cub::Sum(), (uint64_t)0,
-                                           (int64_t)npat, stream));
+                                           (int64_t)(npat + 1), stream));
   rc = idx->ws_scan.ensure(tmp_bytes + 16);
   if (rc) return rc;
   CSFM_CUDA(cub::DeviceScan::ExclusiveScan(idx->ws_scan.p, tmp_bytes, d_row_cnt, d_out_offs, cub::Sum(), (uint64_t)0,
-                                           (int64_t)npat, stream));
+                                           (int64_t)(npat + 1), stream));
   idx->stats.kernel_launches += 2;  // cub scan: init + scan kernels
-  uint64_t* h = reinterpret_cast<uint64_t*>(idx->h_pinned);
-  h[0] = h[1] = 0;
-  CSFM_CUDA(cudaMemcpyAsync(&h[0], d_out_offs + (npat - 1), 8, cudaMemcpyDeviceToHost, stream));
-  CSFM_CUDA(cudaMemcpyAsync(&h[1], d_row_cnt + (npat - 1), 4, cudaMemcpyDeviceToHost, stream));
-  CSFM_CUDA(cudaStreamSynchronize(stream));
-  const uint64_t tot = h[0] + (uint32_t)h[1];
-  *total = tot;
-  h[2] = tot;
-  CSFM_CUDA(cudaMemcpyAsync(d_out_offs + npat, &h[2], 8, cudaMemcpyHostToDevice, stream));
   if (d_status) CSFM_CUDA(cudaMemsetAsync(d_status, 0, npat * 4, stream));
+  uint64_t* h = reinterpret_cast<uint64_t*>(idx->h_pinned) + 16 + (idx->total_slot++ & 15u);  // a slot of its own per call
+  CSFM_CUDA(cudaMemcpyAsync(h, d_out_offs + npat, 8, cudaMemcpyDeviceToHost, stream));
+  CSFM_CUDA(cudaStreamSynchronize(stream));
+  *total = *h;
   return CSFM_OK;
 }
 
@@ -420,6 +420,9 @@ int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, ui
   const uint32_t* d_row_sp = idx->ws_tmp.as<uint32_t>();
   expand_rows_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(d_row_sp, d_out_offs, npat, d_out_pos);
   CSFM_CUDA(cudaGetLastError());
+  if (!idx->ev_ws_tmp) CSFM_CUDA(cudaEventCreateWithFlags(&idx->ev_ws_tmp, cudaEventDisableTiming));
+  CSFM_CUDA(cudaEventRecord(idx->ev_ws_tmp, stream));  // ws_tmp (the intervals) is free again from here on
+  idx->ws_tmp_busy = true;
   idx->stats.kernel_launches += 1;
   return CSFM_OK;
 }

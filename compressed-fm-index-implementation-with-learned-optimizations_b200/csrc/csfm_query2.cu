@@ -587,10 +587,12 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
       const uint32_t avail = cur_end - cur_next;
       const uint32_t my_rank = __popc(need_mask & ((1u << (lane & ~3)) - 1u));
       const uint32_t cnt = __popc(need_mask);
-      if (!active && my_rank < avail) {
+      const bool take = !active && my_rank < avail;
+      uint64_t o0 = 0, o1 = 0;
+      const uint8_t* pb = nullptr;
+      if (take) {
         q = cur_next + my_rank;
         const bool dir = (direct_mask >> cur_buf) & 1u;
-        uint64_t o0, o1;
         if (dir) {
           o0 = a.offs[q];
           o1 = a.offs[q + 1];
@@ -598,16 +600,19 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
           o0 = st.offs[cur_buf][q - cur_base];
           o1 = st.offs[cur_buf][q - cur_base + 1];
         }
-        const uint8_t* pb = st.base_ptr[cur_buf];
-        const uint64_t m = o1 - o0;
+        pb = st.base_ptr[cur_buf];
         mybuf = dir ? 2u : cur_buf;
-        if (!dir && m <= kPrivBytes) {
+        if (!dir && o1 - o0 <= kPrivBytes) {
           // Short pattern of a staged chunk: move it to the sub-warp's private slot so that the
           // chunk buffer can be refilled by TMA while this query is still running.
-          for (uint32_t k = j; k < (uint32_t)m; k += 4) priv[k] = pb[o0 + k];
+          for (uint32_t k = j; k < (uint32_t)(o1 - o0); k += 4) priv[k] = pb[o0 + k];
           pb = priv - o0;
           mybuf = 2u;
         }
+      }
+      __syncwarp();  // the private-slot bytes a lane reads below were written by its three neighbours
+      if (take) {
+        const uint64_t m = o1 - o0;
         active = true;
         if (m == 0) {
           // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
@@ -635,7 +640,6 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
         }
       }
       cur_next += (cnt < avail) ? cnt : avail;
-      __syncwarp();  // private-slot writes of a sub-warp are read by all of its four lanes
     }
     if (exhausted && pf_state == 0 && cur_next >= cur_end && !__any_sync(0xFFFFFFFFu, active)) break;
 
