@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "csfm_host.hpp"
+#include "csfm_kernels.cuh"
 
 namespace csfm {
 
@@ -449,6 +450,50 @@ static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
   return CSFM_OK;
 }
 
+// ---- single-query path -------------------------------------------------------------------------
+// One launch, no copies: the pattern rides in the kernel parameters, the kernel writes count and interval
+// to mapped pinned memory and then the sequence number this thread spins on. Caller holds idx->mu.
+namespace {
+constexpr size_t kSingleResultAt = 512;  // byte offset of the SingleResult inside h_pinned
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+}
+
+bool single_path_ok(const csfm_index* idx, uint64_t len) {
+  return idx->view.layout == kLayoutNibble128 && len <= kSingleMax && idx->instr_mask == 0 && idx->d_pinned != nullptr;
+}
+
+int count_single(csfm_index* idx, const uint8_t* bytes, uint32_t len, uint64_t* count, uint64_t* sp, uint64_t* ep) {
+  SingleQuery q;
+  if (len) std::memcpy(q.bytes, bytes, len);
+  q.len = len;
+  q.seq = ++idx->single_seq;
+  if (q.seq == 0) q.seq = ++idx->single_seq;  // 0 is the value of a fresh result slot
+  auto* d_res = reinterpret_cast<SingleResult*>(static_cast<uint8_t*>(idx->d_pinned) + kSingleResultAt);
+  volatile SingleResult* res = reinterpret_cast<volatile SingleResult*>(static_cast<uint8_t*>(idx->h_pinned) + kSingleResultAt);
+  launch_count_single2(idx->view, q, d_res, idx->stream);
+  CSFM_CUDA(cudaGetLastError());
+  for (uint32_t spins = 1; res->seq != q.seq; ++spins) {
+    cpu_relax();
+    if ((spins & 0x3FFFu) == 0) {  // a failed launch never writes the flag: ask the stream now and then
+      const cudaError_t e = cudaStreamQuery(idx->stream);
+      if (e != cudaErrorNotReady && e != cudaSuccess) return fail(CSFM_ERR_CUDA, std::string("single-query kernel: ") + cudaGetErrorString(e));
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  *count = res->count;
+  if (sp) *sp = res->sp;
+  if (ep) *ep = res->ep;
+  idx->stats.kernel_launches += 1;
+  idx->stats.h2d_bytes = len;  // as kernel parameters
+  idx->stats.d2h_bytes = sizeof(SingleResult);
+  return CSFM_OK;
+}
+}  // namespace
+
 int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
                             uint64_t* d_counts, uint64_t* d_sp_ep, void* stream) {
   if (!idx || (npat && (!d_offs || !d_counts))) return fail(CSFM_ERR_INVALID, "null argument");
@@ -467,6 +512,13 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
   DeviceGuard g(idx->device);
   std::lock_guard<std::mutex> lk(idx->mu);
+  if (npat == 1 && offs[1] >= offs[0] && single_path_ok(idx, offs[1] - offs[0])) {  // cs::FMIndex::count(pattern)
+    std::memset(&idx->stats, 0, sizeof idx->stats);
+    uint64_t sp = 0, ep = 0;
+    const int rc1 = count_single(idx, bytes + offs[0], (uint32_t)(offs[1] - offs[0]), counts, &sp, &ep);
+    if (rc1 == CSFM_OK && sp_ep) { sp_ep[0] = sp; sp_ep[1] = ep; }
+    return rc1;
+  }
   begin_call(idx);
   cudaStream_t st = idx->stream;
   // input staging: [offs (npat+1) u64][bytes]
@@ -678,6 +730,48 @@ int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* off
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
   DeviceGuard g(idx->device);
   std::lock_guard<std::mutex> lk(idx->mu);
+  if (npat == 1 && offs[1] >= offs[0] && single_path_ok(idx, offs[1] - offs[0]) && limit <= 0xFFFFFFFFull) {
+    // cs::FMIndex::locate(pattern): the interval from the single-query kernel (remembered between the
+    // sizing call and the fill call), then one walk launch over the rows sp .. sp + min(count, limit)
+    std::memset(&idx->stats, 0, sizeof idx->stats);
+    const uint8_t* pat = bytes + offs[0];
+    const uint32_t len = (uint32_t)(offs[1] - offs[0]);
+    csfm_index::SingleCache& sc = idx->single_cache;
+    if (!(sc.valid && sc.len == len && std::memcmp(sc.bytes, pat, len) == 0)) {
+      uint64_t cnt = 0, sp = 0;
+      const int rc1 = count_single(idx, pat, len, &cnt, &sp, nullptr);
+      if (rc1) return rc1;
+      sc.valid = true;
+      sc.len = len;
+      if (len) std::memcpy(sc.bytes, pat, len);
+      sc.sp = sp;
+      sc.count = len ? cnt : 0;  // locate("") is empty (fm_index.cpp:109)
+    }
+    const uint64_t tot = std::min<uint64_t>(sc.count, limit);
+    out_offs[0] = 0;
+    out_offs[1] = tot;
+    *total = tot;
+    if (status) status[0] = 0;
+    const bool sizing1 = (out_pos == nullptr && cap == 0);
+    if (sizing1) return CSFM_OK;
+    if (cap < tot) return fail(CSFM_ERR_CAPACITY, "locate output buffer too small");
+    if (tot == 0) return CSFM_OK;
+    int rc1 = idx->ws_pos.ensure((tot + 1) * 8);
+    if (rc1) return rc1;
+    uint64_t* d_pos = idx->ws_pos.as<uint64_t>();
+    int32_t* d_stat = reinterpret_cast<int32_t*>(d_pos + tot);
+    cudaStream_t s1 = idx->stream;
+    CSFM_CUDA(cudaMemsetAsync(d_stat, 0, 8, s1));
+    rc1 = locate_walk(idx, 1, nullptr, d_pos, 0, tot, d_stat, s1, (int64_t)sc.sp);
+    if (rc1) return rc1;
+    CSFM_CUDA(cudaMemcpyAsync(out_pos, d_pos, tot * 8, cudaMemcpyDeviceToHost, s1));
+    int32_t st1 = 0;
+    CSFM_CUDA(cudaMemcpyAsync(&st1, d_stat, 4, cudaMemcpyDeviceToHost, s1));
+    CSFM_CUDA(cudaStreamSynchronize(s1));
+    if (status) status[0] = st1;
+    idx->stats.d2h_bytes = tot * 8 + 4;
+    return CSFM_OK;
+  }
   begin_call(idx);
   cudaStream_t st = idx->stream;
   const size_t offs_bytes = (npat + 1) * 8;

@@ -353,7 +353,11 @@ int index_finish_handle(csfm_index* idx) {
     CSFM_CUDA(cudaMalloc(&idx->d_counters, kCounterSlots * kCounterWords * sizeof(unsigned long long)));
     CSFM_CUDA(cudaMemset(idx->d_counters, 0, kCounterSlots * kCounterWords * sizeof(unsigned long long)));
   }
-  if (!idx->h_pinned) CSFM_CUDA(cudaHostAlloc(&idx->h_pinned, 4096, cudaHostAllocDefault));
+  if (!idx->h_pinned) {
+    CSFM_CUDA(cudaHostAlloc(&idx->h_pinned, 4096, cudaHostAllocMapped));
+    std::memset(idx->h_pinned, 0, 4096);
+    CSFM_CUDA(cudaHostGetDevicePointer(&idx->d_pinned, idx->h_pinned, 0));
+  }
   return CSFM_OK;
 }
 

@@ -69,7 +69,15 @@ struct csfm_index {
   csfm::DeviceBuffer ws_in, ws_out, ws_tmp, ws_scan, ws_pos;
   unsigned long long* d_counters = nullptr;  // ring of work cursors / accumulators
   uint32_t counter_slot = 0;
-  void* h_pinned = nullptr;  // small pinned scratch (totals, stats)
+  void* h_pinned = nullptr;  // small pinned scratch (totals, stats), mapped: the single-query kernel writes its result here
+  void* d_pinned = nullptr;  // device alias of h_pinned
+  uint32_t single_seq = 0;   // sequence number of the last single-query launch
+  struct SingleCache {       // interval of the last single-pattern locate: the sizing call and the fill call search once
+    bool valid = false;
+    uint32_t len = 0;
+    uint8_t bytes[256];
+    uint64_t sp = 0, count = 0;
+  } single_cache;
 
   uint32_t instr_mask = 0;
   bool tma_staging = false;  // count kernel variant (csfm_set_option / CSFM_PATTERN_STAGING=tma)
@@ -108,8 +116,9 @@ int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, ui
                   cudaStream_t stream);
 // ... then rows -> text positions for the slots [first, first + count): LF walks, or one gather per row
 // when the index carries its whole suffix array
+// row_base >= 0: slot i starts at SA row row_base + i (one query's interval) instead of the row stored in d_out_pos[i]
 int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t first,
-                uint64_t count, int32_t* d_status, cudaStream_t stream);
+                uint64_t count, int32_t* d_status, cudaStream_t stream, int64_t row_base = -1);
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream);
 // d_offs[0..count) = exclusive prefix sum of d_lens[0..count) (u8 lengths -> u64 offsets), on `stream`
 int offsets_from_lengths8(const uint8_t* d_lens, uint64_t count, uint64_t* d_offs, DeviceBuffer& scratch,

@@ -219,7 +219,23 @@ struct CountArgs {
   unsigned long long* steps_total;  // nullable (instrumentation)
 };
 
+// Single-query path (cs::FMIndex::count / locate called one pattern at a time, tools/benchmark.cpp): the
+// pattern travels as a kernel PARAMETER and the result comes back through mapped pinned memory that
+// the host spins on, so a query is one launch: no staging copies, no stream synchronisation.
+constexpr uint32_t kSingleMax = 240;
+struct SingleQuery {
+  uint8_t bytes[kSingleMax];
+  uint32_t len;
+  uint32_t seq;  // written to SingleResult::seq last: the host waits for it
+};
+struct SingleResult {
+  unsigned long long count, sp, ep;
+  unsigned int seq, pad;
+};
+
 struct WalkArgs {
+  uint32_t row_base;       // rows_implicit: slot i starts at SA row row_base + i (single-query locate) ...
+  uint32_t rows_implicit;  // ... instead of reading its row from out_pos[i]
   uint64_t* out_pos;  // in: SA row, out: text position
   unsigned long long first;  // this launch walks the output slots [first, first + total)
   unsigned long long total;
@@ -233,6 +249,7 @@ struct WalkArgs {
 // Layout-2 kernels (csfm_query2.cu); launched by the dispatchers in csfm_query.cu.
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging);
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
+void launch_count_single2(const IndexView& iv, const SingleQuery& q, SingleResult* d_result, cudaStream_t stream);
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
 int max_blocks_per_sm_count2(bool tma_staging, const IndexView& iv, const CountArgs& a);
 int max_blocks_per_sm_walk2();

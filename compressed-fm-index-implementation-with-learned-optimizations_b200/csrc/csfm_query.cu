@@ -207,7 +207,7 @@ walk_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkAr
     const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
     if (item != ~0ull) {
       slot = a.first + item;
-      start = (uint32_t)a.out_pos[slot];
+      start = a.rows_implicit ? a.row_base + (uint32_t)slot : (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
       if (row_is_sampled(iv, start)) {
@@ -408,10 +408,10 @@ int locate_plan(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs,
 // smallest byte, so the LF walk from row r ends at (sample + steps) % n == SA[r] and never fails):
 // the position of a row is one gather instead of ~stride LF steps.
 __global__ void rows_to_positions_kernel(const uint32_t* __restrict__ sa, uint64_t* __restrict__ out_pos,
-                                         unsigned long long total) {
+                                         unsigned long long total, uint32_t row_base, uint32_t rows_implicit) {
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
        i += (unsigned long long)gridDim.x * blockDim.x)
-    out_pos[i] = sa[(uint32_t)out_pos[i]];
+    out_pos[i] = sa[rows_implicit ? row_base + (uint32_t)i : (uint32_t)out_pos[i]];
 }
 
 int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t total,
@@ -428,12 +428,15 @@ int locate_expand(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, ui
 }
 
 int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint64_t* d_out_pos, uint64_t first,
-                uint64_t count, int32_t* d_status, cudaStream_t stream) {
+                uint64_t count, int32_t* d_status, cudaStream_t stream, int64_t row_base) {
   if (npat == 0 || count == 0) return CSFM_OK;
+  const uint32_t rows_implicit = row_base >= 0 ? 1u : 0u;
   if (idx->view.dense && idx->view.dense_shift == 0 && !idx->no_sa_locate) {
     const bool timed_sa = (idx->instr_mask & 2u) != 0;
     if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-    rows_to_positions_kernel<<<idx->num_sms * 8, 256, 0, stream>>>(idx->view.dense, d_out_pos + first, count);
+    const int g = (int)std::min<uint64_t>((count + 255) / 256, (uint64_t)idx->num_sms * 8);
+    rows_to_positions_kernel<<<g, 256, 0, stream>>>(idx->view.dense, d_out_pos + first, count, (uint32_t)std::max<int64_t>(row_base, 0) + (uint32_t)first,
+                                                    rows_implicit);
     if (timed_sa) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
     CSFM_CUDA(cudaGetLastError());
     idx->stats.kernel_launches += 1;
@@ -442,6 +445,8 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   unsigned long long* ctr = next_counter_slot(idx);
   CSFM_CUDA(cudaMemsetAsync(ctr, 0, kCounterWords * sizeof(unsigned long long), stream));
   WalkArgs w{};
+  w.row_base = (uint32_t)std::max<int64_t>(row_base, 0);
+  w.rows_implicit = rows_implicit;
   w.out_pos = d_out_pos;
   w.first = first;
   w.total = count;

@@ -671,6 +671,92 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// count for ONE pattern: one warp, the pattern in the kernel parameters, the result (count and interval)
+// written to mapped pinned host memory followed by the sequence number the host is spinning on.
+// Same search as count2_kernel<false,.>: k-mer table for the last k characters, then one rank step per
+// character (fm_index.cpp:79-101).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ SingleQuery sq, SingleResult* __restrict__ res) {
+  __shared__ uint4 ent[kSingleMax];  // per pattern character: x = base, y = code | absent << 31, z = start1[hi], w = C[byte]
+  const int lane = threadIdx.x;
+  const int j = lane & 3;
+  const BlobHeader* __restrict__ h = iv.hdr;
+  const uint32_t m = sq.len;
+  const bool two = iv.L == 2;
+  // every table entry the query will need, fetched at once: two dependent rounds of L2 hits instead of two per step
+  for (uint32_t i = lane; i < m; i += 32) {
+    const uint32_t b = sq.bytes[i];
+    const uint32_t c0 = h->C[b], c1 = h->C[b + 1];
+    const uint32_t code = h->code_of_byte[b];
+    ent[i] = make_uint4(h->base_by_byte[b], code | (c1 == c0 ? 0x80000000u : 0u), h->start1[code >> 4], c0);
+  }
+  __syncwarp();
+  uint32_t sp = 0, ep = 0;
+  unsigned long long cnt = 0;
+  if (m == 0) {
+    cnt = iv.n;  // count("") == n (fm_index.cpp:80)
+  } else {
+    int i;  // index of the next character to prepend
+    const uint32_t kk = iv.kmer_k;
+    bool alive = true;
+    if (kk != 0 && m >= kk) {
+      uint32_t e = 0, mul = 1;
+      for (uint32_t t = 0; t < kk; ++t) {
+        const uint4 x = ent[m - 1 - t];
+        alive = alive && !(x.y & 0x80000000u);
+        e += (x.y & 0xFFu) * mul;
+        mul *= iv.kmer_radix;
+      }
+      if (alive) {
+        if (iv.kmer_tiled) {
+          const uint32_t* const t32 = reinterpret_cast<const uint32_t*>(iv.kmer);
+          sp = t32[e];
+          ep = t32[(size_t)e + 1];
+        } else {
+          const uint2 se = iv.kmer[e];
+          sp = se.x;
+          ep = se.y;
+        }
+      }
+      i = (int)m - 1 - (int)kk;
+    } else {
+      const uint4 x = ent[m - 1];
+      sp = x.w;  // first step needs no rank: [C[c], C[c+1])
+      ep = h->C[(uint32_t)sq.bytes[m - 1] + 1];
+      i = (int)m - 2;
+    }
+    alive = alive && sp < ep;
+    const uint8_t* const lv0 = iv.levels + j * 32;
+    const uint8_t* const lv_last = iv.levels_last + j * 32;
+    const bool mine = lane < 4;
+    for (; i >= 0 && alive; --i) {  // warp-uniform: every lane holds the same sp/ep after the shuffles of its group
+      const uint4 x = ent[i];
+      if (x.y & 0x80000000u) { alive = false; break; }
+      uint32_t rs, re, s1 = sp, e1 = ep;
+      if (two) {
+        rank_pair(lv0, (x.y & 0xFFu) >> 4, sp, ep, mine, j, rs, re);
+        s1 = x.z + rs;
+        e1 = x.z + re;
+      }
+      rank_pair(lv_last, x.y & 15u, s1, e1, mine, j, rs, re);
+      sp = __shfl_sync(0xFFFFFFFFu, x.x + rs, 0);
+      ep = __shfl_sync(0xFFFFFFFFu, x.x + re, 0);
+      alive = sp < ep;
+    }
+    if (alive) cnt = ep - sp;
+    else sp = ep = 0;
+  }
+  if (lane == 0) {
+    res->count = cnt;
+    res->sp = sp;
+    res->ep = ep;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int*>(&res->seq) = sq.seq;
+  }
+}
+
 // One level of access(p) fused with rank (both read the same line): returns the symbol at p in
 // `v` and rank_l(v, p) as the function value. All 32 lanes must call it (shuffles).
 __device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane,
@@ -732,7 +818,7 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
     const unsigned long long item = queue_take(wq, !active, lane, a.cursor, a.total);
     if (item != ~0ull) {
       slot = a.first + item;
-      start = (uint32_t)a.out_pos[slot];
+      start = a.rows_implicit ? a.row_base + (uint32_t)slot : (uint32_t)a.out_pos[slot];
       steps = 0;
       active = true;
       p = start;
@@ -869,6 +955,9 @@ int build_kmer_table(csfm_index* idx, cudaStream_t stream) {
   return CSFM_OK;
 }
 
+void launch_count_single2(const IndexView& iv, const SingleQuery& q, SingleResult* d_result, cudaStream_t stream) {
+  count_single2_kernel<<<1, 32, 0, stream>>>(iv, q, d_result);
+}
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
   walk2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
 }

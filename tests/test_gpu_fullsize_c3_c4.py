@@ -101,8 +101,61 @@ def test_c3_build_products_certified(c3):
     C = np.zeros(257, np.uint32)
     C[1:] = np.cumsum(hist.cpu().numpy()).astype(np.uint32)
     assert (idx.C_array() == C).all()
-    idx.release_sa()
-    torch.cuda.empty_cache()
+
+
+def test_c3_counts_intervals_and_ordered_locate_vs_sa_checker(c3):
+    """All 10^6 counts AND intervals, and located positions IN ORDER, against the independent checker
+    (binary search over the certified suffix array with direct text comparisons, tests/sa_checker.py):
+    nothing of the engine's index takes part in the expected values."""
+    import torch
+    from sa_checker import DeviceArrayU32, expected_locate, sa_intervals
+    fm, dev, text, idx = c3
+    n = text.numel()
+    npat = 1_000_000
+    bytes_d, offs_d = fm.workloads.sampled_patterns_torch(text, npat, 8, 32, 4, 5)
+    sa = DeviceArrayU32.from_ptr(idx.sa_device_ptr(), n, dev)  # certified by test_c3_build_products_certified
+    lb, ub = sa_intervals(text, sa, bytes_d, offs_d)
+    fast = torch.zeros(npat, dtype=torch.int64, device=dev)
+    plain = torch.zeros(npat, dtype=torch.int64, device=dev)
+    spep = torch.zeros(2 * npat, dtype=torch.int64, device=dev)
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, fast.data_ptr(), 0)
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, plain.data_ptr(), spep.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(fast, ub - lb)     # default kernel (tables + text verification)
+    assert torch.equal(plain, ub - lb)    # stepping kernel
+    se = spep.view(-1, 2)
+    assert torch.equal(se[:, 0], lb) and torch.equal(se[:, 1], ub)
+    # a batch with misses and short patterns: random strings, 1..3-byte patterns, a pattern longer than 32
+    from csfm_b200 import workloads as w
+    import numpy as np
+    rd, ro = w.random_patterns_np(bytes(range(1, 256)), 50_000, 5, 77)
+    extra = [text[5:6], text[100:102], text[1000:1003], text[12345:12345 + 200], text[n - 9:n]]
+    xb = torch.cat([torch.from_numpy(rd).to(dev)] + extra)
+    xo = torch.cat([torch.from_numpy(ro.astype(np.int64)).to(dev),
+                    int(ro[-1]) + torch.cumsum(torch.tensor([e.numel() for e in extra], device=dev), 0)])
+    nx = xo.numel() - 1
+    xlb, xub = sa_intervals(text, sa, xb, xo)
+    xc = torch.zeros(nx, dtype=torch.int64, device=dev)
+    xse = torch.zeros(2 * nx, dtype=torch.int64, device=dev)
+    idx.count_batch_device(xb.data_ptr(), xo.data_ptr(), nx, xc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert torch.equal(xc, xub - xlb)
+    idx.count_batch_device(xb.data_ptr(), xo.data_ptr(), nx, xc.data_ptr(), xse.data_ptr())
+    torch.cuda.synchronize()
+    hit = xub > xlb
+    assert torch.equal(xc, xub - xlb)
+    assert torch.equal(xse.view(-1, 2)[hit, 0], xlb[hit]) and torch.equal(xse.view(-1, 2)[hit, 1], xub[hit])
+    assert int(xse.view(-1, 2)[~hit].abs().sum()) == 0  # empty results are normalised to (0, 0)
+    # locate: positions in SA-row order (sais.hpp:13 order, fm_index.cpp:125-153), limit honoured
+    for limit in (100000, 2):
+        q = 200_000
+        offs, pos, status = _locate_device(idx, bytes_d, offs_d, q, limit, dev)
+        e_offs, e_pos = expected_locate(sa, lb[:q], ub[:q], limit)
+        assert int(status.max()) == 0
+        assert torch.equal(offs, e_offs) and torch.equal(pos, e_pos)
+    offs, pos, status = _locate_device(idx, xb, xo, nx, 1000, dev)
+    e_offs, e_pos = expected_locate(sa, xlb, xub, 1000)
+    assert int(status.max()) == 0 and torch.equal(offs, e_offs) and torch.equal(pos, e_pos)
 
 
 def test_c3_one_million_counts(c3):
@@ -156,11 +209,45 @@ def c4():
     torch.cuda.set_device(dev)
     n = 1 << 28
     text = fm.workloads.dna_text_torch(n, 6, dev)
-    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0)
+    idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0, flags=fm.BUILD_KEEP_SA)
     yield fm, dev, text, idx
     idx.close()
     del text
     torch.cuda.empty_cache()
+
+
+def test_c4_one_million_patterns_ordered_locate_vs_sa_checker(c4):
+    """configs[3] at its stated size: 1 M text-sampled patterns of length 10 (~257 occurrences each, ~2.6e8
+    positions), every count, interval and position IN ORDER against the independent checker."""
+    import torch
+    from sa_checker import DeviceArrayU32, expected_locate, sa_intervals
+    fm, dev, text, idx = c4
+    n = text.numel()
+    cert = fm.workloads.certify_sa_torch(text, idx.sa_device_ptr(), n)
+    assert cert["ok"], cert
+    sa = DeviceArrayU32.from_ptr(idx.sa_device_ptr(), n, dev)
+    npat, plen = 1_000_000, 10
+    bytes_d, offs_d = fm.workloads.sampled_patterns_torch(text, npat, plen, plen, 0, 8)
+    lb, ub = sa_intervals(text, sa, bytes_d, offs_d)
+    counts = torch.zeros(npat, dtype=torch.int64, device=dev)
+    spep = torch.zeros(2 * npat, dtype=torch.int64, device=dev)
+    idx.count_batch_device(bytes_d.data_ptr(), offs_d.data_ptr(), npat, counts.data_ptr(), spep.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(counts, ub - lb)
+    assert torch.equal(spep.view(-1, 2)[:, 0], lb) and torch.equal(spep.view(-1, 2)[:, 1], ub)
+    del spep
+    offs, pos, status = _locate_device(idx, bytes_d, offs_d, npat, 100000, dev)
+    assert int(status.max()) == 0
+    e_offs, e_pos = expected_locate(sa, lb, ub, 100000)
+    assert torch.equal(offs, e_offs)
+    assert torch.equal(pos, e_pos)
+    del pos, e_pos
+    # secondary set of the config: length 12 (~17 occurrences each), small limit
+    b12, o12 = fm.workloads.sampled_patterns_torch(text, 200_000, 12, 12, 0, 9)
+    lb12, ub12 = sa_intervals(text, sa, b12, o12)
+    offs, pos, status = _locate_device(idx, b12, o12, 200_000, 7, dev)
+    e_offs, e_pos = expected_locate(sa, lb12, ub12, 7)
+    assert int(status.max()) == 0 and torch.equal(offs, e_offs) and torch.equal(pos, e_pos)
 
 
 def test_c4_locate_full_size(c4):
