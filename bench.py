@@ -160,6 +160,60 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+L2_RESIDENT_BYTES = 126 << 20   # an index up to the L2 size is served mostly from it (profiles/r2_l2_sweep_probe.json: graceful decay past 64 MiB)
+RANDOM_FETCH_CEILING = 37.3e9    # random 128-byte line fetches/s out of HBM (profiles/r1_gather_probe.json, 4 GiB buffer)
+
+
+def kernel_sources_sha16():
+    """Identifies the kernel sources a committed ncu capture belongs to (.git does not travel to the GPU box)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "compressed-fm-index-implementation-with-learned-optimizations_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".hpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(key, kernel_name):
+    """dram__bytes_read + write per launch from profiles/count_kernel_traffic.json (written by tools/ncu_traffic.py from an
+    `ncu --set full` capture) -- but only when that capture was taken from the kernel sources in this tree and names the
+    kernel this run launches; a stale or foreign capture must not decorate a new kernel. -> (bytes | None, meta)"""
+    tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    try:
+        doc = json.load(open(tp))
+        ent = doc.get("captures", {}).get(key)
+        if not ent:
+            return None, {"valid": False, "why": f"no capture for {key}"}
+        sha = kernel_sources_sha16()
+        base = kernel_name.split("<")[0]
+        if doc.get("source_sha16") != sha:
+            return None, {"valid": False, "why": f"capture belongs to sources {doc.get('source_sha16')}, this tree is {sha}"}
+        if base not in ent.get("kernel", ""):
+            return None, {"valid": False, "why": f"capture is of {ent.get('kernel')}, this run launches {kernel_name}"}
+        meta = {"valid": True, "source_sha16": sha}
+        meta.update({k: v for k, v in ent.items() if k != "dram_bytes_per_launch"})
+        return float(ent["dram_bytes_per_launch"]), meta
+    except Exception as e:
+        return None, {"valid": False, "why": repr(e)}
+
+
+def l2_random_peak(index_bytes, line_bytes):
+    """Measured random-fetch ceiling (GB/s of `line_bytes` units, dependent chains) for a working set of this size."""
+    try:
+        doc = json.load(open(os.path.join(ROOT, "profiles", "r2_l2_sweep_probe.json")))
+        rows = [r for r in doc["results"] if r["ctas_per_sm"] == 8 and r["unit_bytes"] == line_bytes]
+        rows.sort(key=lambda r: r["buffer_mib"])
+        for r in rows:
+            if (r["buffer_mib"] << 20) >= index_bytes:
+                return float(r["gbytes_per_s"]), (f"measured: profiles/r2_l2_sweep_probe.json, {r['buffer_mib']} MiB working set, "
+                                                 f"{line_bytes}-byte units, {r['gunits_per_s']:.0f} G fetches/s")
+    except Exception:
+        pass
+    return 144.0 * line_bytes, "fallback: 144 G random 128-byte fetches/s measured on a 32 MiB working set (round 1 probe)"
+
+
 def make_text(wl, n, device):
     from csfm_b200 import workloads as w
     return (w.byte_text_torch if wl["kind"] == "byte" else w.dna_text_torch)(n, wl["seed_text"], device)
@@ -315,7 +369,7 @@ def locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, budget_s):
             "bit_exact_vs_gpu": ok}
 
 
-def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, limit=100_000, iters=5, cpu_budget=0.0):
+def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10, limit=100_000, iters=5, cpu_budget=0.0):
     """locate_batch on device-resident inputs/outputs: occurrences/s, checked by re-reading the text.
 
     Weak scaling like the count leg: rank 0 builds the index, one broadcast replicates it, every rank
@@ -393,19 +447,36 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
         idx.close()
         return None
     L, lb = int(info.levels), int(info.line_bytes)
+    # executed fetches are exact here: every LF step loads exactly L level lines, every occurrence one sample sector
+    # and writes 8 bytes (sum over occurrences of w x L x line + 32 + 8)
     alg = lf_all * L * lb + total_all * 40
-    peak, _ = measured_peak()
-    out = {"metric": "locate occurrences/sec", "value": total_all / (ms / 1e3), "unit": "occurrences/s", "n_gpus": world,
+    peak, peak_src = measured_peak()
+    t_s = ms / 1e3
+    kname = {1: "walk_kernel", 2: "walk2_kernel", 3: "walk3_kernel"}.get(int(info.layout), "walk_kernel")
+    traffic, tmeta = committed_traffic("c4_walk", kname)
+    in_l2 = int(info.blob_bytes) <= L2_RESIDENT_BYTES
+    ws_peak, ws_src = l2_random_peak(int(info.blob_bytes), lb)
+    achieved_exec = alg / world / t_s / 1e9
+    if in_l2:
+        roof = {"bound": "l2", "achieved": achieved_exec, "peak": ws_peak, "frac": achieved_exec / ws_peak, "peak_source": ws_src,
+                "frac_basis": "executed line fetches x line bytes over the measured random-fetch ceiling for a working set of this size"}
+    else:
+        ach = (traffic / t_s / 1e9) if traffic else achieved_exec
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "frac": ach / peak, "peak_source": peak_src,
+                "frac_basis": "dram traffic (ncu) / duration" if traffic else
+                "executed line fetches x line bytes / duration (part of them hit the L2: no valid ncu capture to subtract them)",
+                "random_fetch_ceiling_at_this_working_set_gbs": ws_peak, "frac_of_that_ceiling": achieved_exec / ws_peak,
+                "ceiling_source": ws_src}
+    roof.update({"kernel": kname, "unit": "GB/s", "traffic": traffic, "traffic_capture": tmeta,
+                 "executed": {"bytes_per_batch": alg / world, "gbs": achieved_exec, "level_lines_per_s": lf_all * L / world / t_s},
+                 "note": "per GPU; time covers count pass + scan + expand + walk"})
+    out = {"metric": "locate occurrences/sec", "value": total_all / t_s, "unit": "occurrences/s", "n_gpus": world,
            "ms_per_batch": ms, "scaling": "weak",
-           "config": {"workload": f"C4-style: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen} per GPU, limit {limit}",
-                      "levels": L, "line_bytes": lb, "index_bytes": int(info.blob_bytes), "index_build_s": build_s,
+           "config": {"workload": f"C4: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen} per GPU, limit {limit}",
+                      "levels": L, "line_bytes": lb, "layout": int(info.layout), "index_bytes": int(info.blob_bytes), "index_build_s": build_s,
                       "index_broadcast_ms": bcast_ms},
            "occurrences_per_batch": int(total_all), "lf_steps_per_occurrence": lf_all / max(1, total_all),
-           "roofline": {"bound": "hbm", "kernel": "walk2_kernel" if int(info.layout) == 2 else "walk_kernel",
-                        "achieved": alg / world / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / world / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_batch": alg / world,
-                        "note": "per GPU: sum over occurrences of LF steps x L x line bytes + 32 B sample + 8 B output; time covers count "
-                                "pass + scan + expand + walk. Above 1 because about a quarter of the line fetches hit the L2"},
+           "roofline": roof,
            "checks": {"positions_verified_against_text": positions_ok, "all_counts_ge_1": counts_ok, "failed_queries": 0}}
 
     # ---- the same batch through the host-pointer call (pinned buffers; H2D and D2H inside the timed region)
@@ -492,17 +563,28 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=200_000, plen=10, l
 # ------------------------------------------------------------------------------------------------
 # engine arm
 # ------------------------------------------------------------------------------------------------
-def run_engine(args, rank, world, local_rank):
+def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
+    """One count workload end to end: text, index (built on rank 0, one broadcast), resident batches, the
+    device-resident timed region, the host-pointer e2e region, roofline, CPU baseline. `full` adds the
+    comparison legs of the headline line (stepping-only kernel, large-table index, every e2e form).
+    Returns the JSON object on rank 0, None elsewhere. Frees everything it allocated."""
     import torch
     import torch.distributed as dist
     import csfm_b200 as fm
 
-    wl = dict(WORKLOADS[args.workload])
-    n = text_size(args, wl)
+    wl = dict(WORKLOADS[wl_name])
+    n = text_size(args, wl) if wl_name == args.workload else wl.get("n", 1 << wl["n_log2"])
     batch = args.batch or wl["batch"]
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     fm.lib()  # fail loudly if the CUDA extension is missing
+
+    class _A:  # the leg's own step counts under the names the body uses
+        pass
+    largs = _A()
+    largs.__dict__.update(vars(args))
+    largs.steps, largs.warmup, largs.workload = steps, warmup, wl_name
+    args = largs
 
     def barrier():
         if world > 1:
@@ -562,11 +644,12 @@ def run_engine(args, rank, world, local_rank):
 
     # exact executed-step counts per batch (S of the roofline model) + correctness properties
     idx.set_instrumentation(1)
-    steps_per_batch, lookups_per_batch, checks_per_batch, halves_per_batch = [], [], [], []
+    steps_per_batch, lookups_per_batch, checks_per_batch, halves_per_batch, lines_per_batch = [], [], [], [], []
     for b in range(NB):
         step_device(b)
         stream.synchronize()
         steps_per_batch.append(int(idx.last_call_stats().search_steps))
+        lines_per_batch.append(int(idx.last_call_stats().line_fetches))
         lookups_per_batch.append(int(idx.last_call_stats().table_lookups))
         checks_per_batch.append(int(idx.last_call_stats().text_checks))
         halves_per_batch.append(int(idx.last_call_stats().half_steps))
@@ -598,7 +681,7 @@ def run_engine(args, rank, world, local_rank):
     # ---- the stepping-only kernel on the same index (count2_kernel<false>): asking for the [sp,ep)
     # intervals rules the text verification out, so every query runs the plain backward search
     stepping = None
-    if int(info.text_check) and int(info.layout) == 2:
+    if full and int(info.text_check) and int(info.layout) == 2:
         d_spep = torch.zeros(2 * batch, dtype=torch.int64, device=dev)
 
         def step_plain(b):
@@ -611,6 +694,7 @@ def run_engine(args, rank, world, local_rank):
         stream.synchronize()
         plain_steps = int(idx.last_call_stats().search_steps)
         plain_lookups = int(idx.last_call_stats().table_lookups)
+        plain_lines = int(idx.last_call_stats().line_fetches)
         idx.set_instrumentation(0)
         plain_equal = bool((d_counts.cpu().numpy() == c0).all())
         K2 = min(args.steps, 40)
@@ -626,7 +710,8 @@ def run_engine(args, rank, world, local_rank):
         plain_ms = e0.elapsed_time(e1) / K2
         stepping = {"kernel": "count2_kernel<false,false>", "ms_per_launch": plain_ms, "launches_timed": K2,
                     "queries_per_s": batch / (plain_ms / 1e3), "search_steps_per_launch": plain_steps,
-                    "table_lookups_per_launch": plain_lookups, "counts_equal_default_kernel": plain_equal}
+                    "table_lookups_per_launch": plain_lookups, "level_lines_fetched_per_launch": plain_lines,
+                    "counts_equal_default_kernel": plain_equal}
         launches += K2 + 4
         del d_spep
 
@@ -634,7 +719,7 @@ def run_engine(args, rank, world, local_rank):
     # for a byte alphabet k goes from 3 to 4 (2^32 entries, 17 GB), the lookup leaves ~1 row and the query
     # goes straight to the text verification: one table line + one suffix-array line + one text line
     large = None
-    if world == 1 and not args.no_large_table and not args.large_table and int(info.layout) == 2 and torch.cuda.mem_get_info()[0] > 100e9:
+    if full and world == 1 and not args.no_large_table and not args.large_table and int(info.layout) == 2 and torch.cuda.mem_get_info()[0] > 100e9:
         try:
             t0 = time.perf_counter()
             idx_big = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank,
@@ -653,6 +738,7 @@ def run_engine(args, rank, world, local_rank):
             stream.synchronize()
             bst = idx_big.last_call_stats()
             big_steps, big_lookups, big_checks = int(bst.search_steps), int(bst.table_lookups), int(bst.text_checks)
+            big_lines = int(bst.line_fetches)
             idx_big.set_instrumentation(0)
             big_equal = bool((d_counts_big.cpu().numpy() == c0).all())
             K3 = min(args.steps, 100)
@@ -671,6 +757,7 @@ def run_engine(args, rank, world, local_rank):
                      "index_build_s": big_build_s, "ms_per_launch": big_ms, "launches_timed": K3,
                      "queries_per_s": batch / (big_ms / 1e3), "search_steps_per_launch": big_steps,
                      "table_lookups_per_launch": big_lookups, "text_checks_per_launch": big_checks,
+                     "level_lines_fetched_per_launch": big_lines,
                      "algorithmic_bytes_per_launch": big_bytes, "achieved_gbs": big_bytes / (big_ms / 1e3) / 1e9,
                      "counts_equal_default_index": big_equal,
                      "note": "opt-in build: the k-mer table takes up to 40 GiB of the 180 GB (k = 4 on bytes, 13 on DNA+$), a query is "
@@ -727,7 +814,7 @@ def run_engine(args, rank, world, local_rank):
 
     e2e_steps = args.steps
     e2e_times, e2e_bytes = {}, {}
-    for form in ("u64", "u32", "len8"):
+    for form in (("u64", "u32", "len8") if full else ("len8",)):
         e2e_run(max(3, args.warmup), form)
         torch.cuda.synchronize()
         barrier()
@@ -739,131 +826,165 @@ def run_engine(args, rank, world, local_rank):
         stf = idx.last_call_stats()
         e2e_bytes[form] = (int(stf.h2d_bytes), int(stf.d2h_bytes))
     h2d32, d2h32 = e2e_bytes["len8"]
-    e2e_s_u32 = e2e_times["u32"]
-    e2e_s, e2e_s_u64 = e2e_times["len8"], e2e_times["u64"]
+    e2e_s = e2e_times["len8"]
+    e2e_s_u32, e2e_s_u64 = e2e_times.get("u32", 0.0), e2e_times.get("u64", 0.0)
     last = (e2e_steps - 1) % DEPTH
-    compact_equal = bool((h_out32[last].numpy().astype(np.int64) == h_out[last].numpy()).all() and
-                         (h_out8[last].numpy().astype(np.int64) == h_out[last].numpy()).all())
-    h_counts = h_out[(e2e_steps - 1) % DEPTH]
-    # the synchronous call (csfm_count_batch) for comparison: one step at a time, nothing overlapped
-    h_sync = torch.zeros(batch, dtype=torch.int64).pin_memory()
-    L_ = fm.lib()
-    for i in range(3):  # warm-up: first call creates the slice streams and sizes the workspace
-        hb, ho = h_batches[i % NB]
-        L_.csfm_count_batch(idx._h, hb.data_ptr(), ho.data_ptr(), batch, h_sync.data_ptr(), None)
-    t0 = time.perf_counter()
-    for i in range(min(20, e2e_steps)):
-        hb, ho = h_batches[i % NB]
-        if L_.csfm_count_batch(idx._h, hb.data_ptr(), ho.data_ptr(), batch, h_sync.data_ptr(), None) != 0:
-            raise RuntimeError(L_.csfm_last_error().decode())
-    e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / min(20, e2e_steps)
-    st = idx.last_call_stats()
-    h2d64, d2h64 = int(st.h2d_bytes), int(st.d2h_bytes)
     h2d, d2h = h2d32, d2h32
+    e2e_sync_ms = h2d64 = d2h64 = None
+    compact_equal = None
+    if full:
+        compact_equal = bool((h_out32[last].numpy().astype(np.int64) == h_out[last].numpy()).all() and
+                             (h_out8[last].numpy().astype(np.int64) == h_out[last].numpy()).all())
+        # the synchronous call (csfm_count_batch) for comparison: one step at a time, nothing overlapped
+        h_sync = torch.zeros(batch, dtype=torch.int64).pin_memory()
+        L_ = fm.lib()
+        for i in range(3):  # warm-up: first call creates the slice streams and sizes the workspace
+            hb, ho = h_batches[i % NB]
+            L_.csfm_count_batch(idx._h, hb.data_ptr(), ho.data_ptr(), batch, h_sync.data_ptr(), None)
+        t0 = time.perf_counter()
+        for i in range(min(20, e2e_steps)):
+            hb, ho = h_batches[i % NB]
+            if L_.csfm_count_batch(idx._h, hb.data_ptr(), ho.data_ptr(), batch, h_sync.data_ptr(), None) != 0:
+                raise RuntimeError(L_.csfm_last_error().decode())
+        e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / min(20, e2e_steps)
+        st = idx.last_call_stats()
+        h2d64, d2h64 = int(st.h2d_bytes), int(st.d2h_bytes)
     step_device(e2e_steps - 1)  # same batch as the last end-to-end step: both paths must agree
     stream.synchronize()
-    e2e_equal = bool((h_counts.numpy() == d_counts.cpu().numpy()).all())
+    e2e_equal = bool((h_out8[last].numpy().astype(np.int64) == d_counts.cpu().numpy()).all())
 
-    # ---- locate leg (every rank takes part: weak scaling like the count leg) ---------------------------
-    locate = None
-    if not args.no_locate:
-        try:
-            locate = measure_locate(fm, dev, rank, world,
-                                    cpu_budget=0.0 if (args.no_cpu_baseline or world > 1) else min(args.cpu_budget, 10.0))
-        except Exception as e:  # pragma: no cover
-            if world > 1:
-                raise  # a rank that drops out of the collectives would hang the others
-            locate = {"unavailable": repr(e)}
+    # ---- the ceiling the e2e region is up against: the same bytes per step, copies only (all ranks at once) -------
+    # pinned H2D of (lengths + pattern bytes) and pinned D2H of the u32 counts on two streams, no kernel
+    copy_s = None
+    try:
+        # like the product's three async slots: step i uses stream i % 3, H2D then D2H on that stream
+        h_in = [torch.zeros(h2d, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+        d_in = [torch.empty(h2d, dtype=torch.uint8, device=dev) for _ in range(DEPTH)]
+        d_o = [torch.zeros(d2h, dtype=torch.uint8, device=dev) for _ in range(DEPTH)]
+        h_o = [torch.zeros(d2h, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+        cstreams = [torch.cuda.Stream(device=dev) for _ in range(DEPTH)]
+
+        def copies(k):
+            for i in range(k):
+                with torch.cuda.stream(cstreams[i % DEPTH]):
+                    d_in[i % DEPTH].copy_(h_in[i % DEPTH], non_blocking=True)
+                    h_o[i % DEPTH].copy_(d_o[i % DEPTH], non_blocking=True)
+            for cs_ in cstreams:
+                cs_.synchronize()
+
+        copies(5)
+        barrier()
+        t0 = time.perf_counter()
+        copies(e2e_steps)
+        copy_s = time.perf_counter() - t0
+        barrier()
+        del h_in, d_in, d_o, h_o
+    except Exception as e:  # pragma: no cover
+        log("copy-ceiling probe failed:", repr(e))
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, e2e_s_u64, e2e_s_u32], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_s_u64, e2e_s_u32, copy_s or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s, e2e_s_u64, e2e_s_u32 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        copy_s = float(t[4]) or None
     if rank != 0:
-        return
+        idx.close()
+        del d_batches, h_batches, text
+        torch.cuda.empty_cache()
+        return None
 
     value = world * args.steps * batch / (total_ms / 1e3)
     e2e_value = world * e2e_steps * batch / e2e_s
 
-    # ---- roofline of the dominant kernel (count_kernel) ------------------------------------------------
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------
     peak, peak_src = measured_peak()
     line_bytes = int(info.line_bytes)
-    # executed traffic model: every rank step reads 2 x L lines, every k-mer table lookup one line,
-    # every text verification two (the suffix-array entry and the text window)
-    alg_bytes = [steps_per_batch[i % NB] * 2 * L * line_bytes + halves_per_batch[i % NB] * 2 * line_bytes +
-                 lookups_per_batch[i % NB] * 128 + checks_per_batch[i % NB] * 256 for i in range(args.steps)]
-    achieved = sum(alg_bytes) / (total_ms / 1e3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    t_launch_s = total_ms / args.steps / 1e3
+    mean_of = lambda per_batch: float(np.mean([per_batch[i % NB] for i in range(args.steps)]))
+    steps_m, lookups_m, checks_m, halves_m, lines_m = (mean_of(x) for x in (steps_per_batch, lookups_per_batch, checks_per_batch,
+                                                                            halves_per_batch, lines_per_batch))
+    # (1) the contract's model: every executed rank step reads 2 x L lines, a half step 2 lines, every
+    #     k-mer table lookup one line, every text verification two (suffix-array entry, text window)
+    model_bytes = steps_m * 2 * L * line_bytes + halves_m * 2 * line_bytes + lookups_m * 128 + checks_m * 256
+    # (2) what the launch really asked the memory system for: level lines LOADED (sp and ep share one load when they
+    #     fall in one line; counted by the instrumented kernel) + the same table / verification lines
+    have_lines = lines_m > 0
+    executed_bytes = (lines_m * line_bytes + lookups_m * 128 + checks_m * 256) if have_lines else model_bytes
     kernel_name = ("count2_tma_kernel" if os.environ.get("CSFM_PATTERN_STAGING") == "tma" else
                    ("count2_kernel<true,false>" if int(info.text_check) else "count2_kernel<false,false>")) \
-        if int(info.layout) == 2 else "count_kernel"
-    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": float(np.mean(alg_bytes)),
-                "search_steps_per_launch": float(np.mean([steps_per_batch[i % NB] for i in range(args.steps)])),
-                "table_lookups_per_launch": float(np.mean([lookups_per_batch[i % NB] for i in range(args.steps)])),
-                "text_checks_per_launch": float(np.mean([checks_per_batch[i % NB] for i in range(args.steps)])),
-                "half_steps_per_launch": float(np.mean([halves_per_batch[i % NB] for i in range(args.steps)])),
-                "half_table": int(info.half_table),
-                "kmer_k": int(info.kmer_k), "text_check": int(info.text_check),
-                "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()),
-                "note": "duration per launch = CUDA events on the launching stream around each step "
-                        "(32-byte cursor memset + the count kernel). achieved = executed algorithmic bytes (rank steps x 2 "
-                        "x L x line + table lookups x 128 B + text verifications x 256 B) / duration; sp and ep often "
-                        "share a line, so the real DRAM traffic (`traffic`, ncu) is lower. The binding ceiling is the "
-                        "random 128-byte fetch RATE (frac_of_random_fetch_ceiling), not streaming bandwidth"}
+        if int(info.layout) == 2 else ("count3_kernel" if int(info.layout) == 3 else "count_kernel")
+    # (3) DRAM bytes of one launch from the committed ncu capture, only if it was taken from THESE kernel sources
+    traffic, traffic_meta = committed_traffic(args.workload if not args.large_table else args.workload + "_large_table", kernel_name)
+    in_l2 = int(info.blob_bytes) <= L2_RESIDENT_BYTES
+    if in_l2:
+        l2_peak, l2_src = l2_random_peak(int(info.blob_bytes), line_bytes)
+        achieved = executed_bytes / t_launch_s / 1e9
+        roofline = {"bound": "l2", "kernel": kernel_name, "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
+                    "frac": achieved / l2_peak, "traffic": traffic, "peak_source": l2_src,
+                    "frac_basis": "executed line fetches x line bytes over the measured L2 random-fetch ceiling for a working set of this size",
+                    "hbm_stream_peak": peak}
+    else:
+        basis = "dram traffic (ncu) / duration" if traffic else "executed line fetches x 128 B / duration (no valid ncu capture for these sources)"
+        achieved = (traffic if traffic else executed_bytes) / t_launch_s / 1e9
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "frac_basis": basis,
+                    "line_fetches_per_s": (traffic if traffic else executed_bytes) / 128 / t_launch_s,
+                    "random_fetch_ceiling_lines_per_s": RANDOM_FETCH_CEILING,
+                    "frac_of_random_fetch_ceiling": (traffic if traffic else executed_bytes) / 128 / t_launch_s / RANDOM_FETCH_CEILING}
+    roofline.update({
+        "traffic_capture": traffic_meta,
+        "model": {"bytes_per_launch": model_bytes, "gbs": model_bytes / t_launch_s / 1e9, "frac_of_hbm_peak": model_bytes / t_launch_s / 1e9 / peak,
+                  "note": "SURVEY §8d contract formula: rank steps x 2 x L x line + half steps x 2 x line + lookups x 128 + verifications x 256; "
+                          "double-counts the line sp and ep share, so it can exceed what is fetched"},
+        "executed": {"bytes_per_launch": executed_bytes, "gbs": executed_bytes / t_launch_s / 1e9,
+                     "level_lines_fetched_per_launch": lines_m if have_lines else None},
+        "search_steps_per_launch": steps_m, "table_lookups_per_launch": lookups_m, "text_checks_per_launch": checks_m,
+        "half_steps_per_launch": halves_m, "half_table": int(info.half_table), "kmer_k": int(info.kmer_k),
+        "text_check": int(info.text_check),
+        "kernel_ms_mean": float(step_ms.mean()), "kernel_ms_min": float(step_ms.min()), "kernel_ms_max": float(step_ms.max()),
+        "kernel_ms_p50": float(np.median(step_ms)),
+        "note": "duration per launch = CUDA events on the launching stream around each step (32-byte cursor memset + the count kernel)"})
     # the same launch charged with the REFERENCE algorithm's traffic model: every
-    # character of a text-sampled pattern is one executed step of 2 x L lines there
+    # character of a text-sampled pattern is one executed step of 2 x 8 levels x 64 B there
     ref_steps = float(np.mean([int(d_batches[i % NB][1][-1].item()) for i in range(min(args.steps, NB))]))
-    roofline["reference_model"] = {"steps_per_launch": ref_steps, "bytes_per_launch": ref_steps * 2 * L * line_bytes,
-                                   "gbs": ref_steps * 2 * L * line_bytes / (total_ms / args.steps / 1e3) / 1e9,
-                                   "note": "what the reference's step-by-step search would move for the same batch; the "
-                                           "engine skips most of it (k-mer table, shared lines, text verification)"}
+    roofline["reference_model"] = {"steps_per_launch": ref_steps, "bytes_per_launch": ref_steps * 1024,
+                                   "gbs": ref_steps * 1024 / t_launch_s / 1e9,
+                                   "note": "what the reference's step-by-step search over 8 binary levels would move for the same batch "
+                                           "(1024 B per step); the engine avoids most of it (16-ary levels, k-mer table, shared lines, "
+                                           "text verification), so this is work avoided, not bandwidth achieved"}
     if stepping:
         pb = stepping["search_steps_per_launch"] * 2 * L * line_bytes + stepping["table_lookups_per_launch"] * 128
-        stepping["algorithmic_bytes_per_launch"] = pb
-        stepping["achieved_gbs"] = pb / (stepping["ms_per_launch"] / 1e3) / 1e9
-        stepping["frac"] = stepping["achieved_gbs"] / peak
-        try:
-            t2 = json.load(open(tp)).get(args.workload + "_no_text_check", {}).get("dram_bytes_per_launch")
-        except Exception:
-            t2 = None
-        if t2:
-            stepping["traffic"] = t2
-            stepping["frac_of_random_fetch_ceiling"] = t2 / 128 / (stepping["ms_per_launch"] / 1e3) / 37.3e9
-        stepping["note"] = ("the same batches through the plain backward-search kernel (every character a rank step; "
-                            "selected by asking for the intervals), for comparison with the default kernel above")
+        pe = stepping["level_lines_fetched_per_launch"] * line_bytes + stepping["table_lookups_per_launch"] * 128
+        t2, t2_meta = committed_traffic(args.workload + "_stepping", "count2_kernel<false,false>")
+        ts = stepping["ms_per_launch"] / 1e3
+        stepping.update({"model_bytes_per_launch": pb, "model_gbs": pb / ts / 1e9, "executed_bytes_per_launch": pe,
+                         "executed_gbs": pe / ts / 1e9, "traffic": t2, "traffic_capture": t2_meta,
+                         "achieved_gbs": (t2 if t2 else pe) / ts / 1e9, "frac": (t2 if t2 else pe) / ts / 1e9 / peak,
+                         "frac_basis": "dram traffic (ncu) / duration" if t2 else "executed line fetches x 128 B / duration",
+                         "frac_of_random_fetch_ceiling": (t2 if t2 else pe) / 128 / ts / RANDOM_FETCH_CEILING,
+                         "note": "the plain FM-index kernel on the same batches (every character a rank step; selected by asking for "
+                                 "the intervals): the robust figure that does not depend on the text being random. An index built with "
+                                 "CSFM_BUILD_NO_TEXT_CHECK runs this kernel for every call and carries neither text nor suffix array",
+                         "sa_free_index_bytes": int(info.blob_bytes) - 5 * n - 64})
         roofline["stepping_only"] = stepping
     if large:
         if "achieved_gbs" in large:
-            large["frac"] = large["achieved_gbs"] / peak
-            try:
-                t3 = json.load(open(tp)).get(args.workload + "_large_table", {}).get("dram_bytes_per_launch")
-            except Exception:
-                t3 = None
-            if t3:
-                large["traffic"] = t3
-                large["frac_of_random_fetch_ceiling"] = t3 / 128 / (large["ms_per_launch"] / 1e3) / 37.3e9
+            t3, t3_meta = committed_traffic(args.workload + "_large_table", "count2_kernel<true,false>")
+            tl = large["ms_per_launch"] / 1e3
+            pe = large["level_lines_fetched_per_launch"] * line_bytes + large["table_lookups_per_launch"] * 128 + large["text_checks_per_launch"] * 256
+            large.update({"executed_bytes_per_launch": pe, "traffic": t3, "traffic_capture": t3_meta,
+                          "achieved_gbs": (t3 if t3 else pe) / tl / 1e9, "frac": (t3 if t3 else pe) / tl / 1e9 / peak,
+                          "frac_of_random_fetch_ceiling": (t3 if t3 else pe) / 128 / tl / RANDOM_FETCH_CEILING})
         roofline["large_kmer_table"] = large
-    if traffic:
-        # the ceiling that actually binds: random 128-byte line fetches per second (tools/gather_probe.cu)
-        roofline["dram_gbs_from_traffic"] = traffic / (total_ms / args.steps / 1e3) / 1e9
-        roofline["line_fetches_per_s"] = traffic / 128 / (total_ms / args.steps / 1e3)
-        roofline["random_fetch_ceiling_lines_per_s"] = 37.3e9
-        roofline["frac_of_random_fetch_ceiling"] = roofline["line_fetches_per_s"] / 37.3e9
 
     # ---- CPU baseline: the unmodified reference on the host cores, bounded sample, checked vs the GPU
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.workload == "c5":
-        cpu = {"value": None, "unit": "queries/s", "kind": "reference",
-               "sample": "not run at this size (the reference's index would have to be injected from a 4.3 GB plane set); see c2 / c3"}
+    if world == 1 and not args.no_cpu_baseline and n > (1 << 31):
+        cpu = {"value": None, "unit": "queries/s", "kind": "reference", "cores": os.cpu_count(),
+               "sample": "not run at this size: the reference's own index (text + BWT + 4n-byte SA + 8 bit planes, 7.2 n bytes) would "
+                         "need ~29 GB of host memory injected from the GPU and its rank rescans 0.5 GB per 1-bit: < 0.1 q/s per core "
+                         "(extrapolated from c2 / c3, SURVEY §6); parity at this size is tests/test_gpu_fullsize_c5.py"}
     elif world == 1 and not args.no_cpu_baseline:
         try:
             import oracle
@@ -875,17 +996,55 @@ def run_engine(args, rank, world, local_rank):
             t_inject = time.perf_counter() - t0
             hb, ho = h_batches[0]
             data, offs = hb.numpy(), ho.numpy().astype(np.uint64)
-            out, q, dt = reference_timed_sample(ref, data, offs, args.cpu_budget, nthreads)
+            out, q, dt = reference_timed_sample(ref, data, offs, args.cpu_budget if full else min(args.cpu_budget, 8.0), nthreads)
             ok = bool((out[:q] == c0[:q].astype(np.uint64)).all())
             cpu = {"value": q / dt, "unit": "queries/s", "cores": nthreads, "kind": "reference",
                    "sample": f"first {q} queries of batch 0 in {dt:.1f} s on {nthreads} std::threads (reference index injected in {t_inject:.0f} s)",
                    "bit_exact_vs_gpu": ok}
             if not ok:
                 log("ERROR: GPU counts differ from the reference on the sampled queries")
+            del ref
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
 
+    # independent spot check: a naive scan of the text for a few patterns of batch 0 (no index involved)
+    naive_ok = None
+    try:
+        naive_ok = True
+        bytes0, offs0 = d_batches[0]
+        for qn in range(4 if n > (1 << 31) else 8):
+            pat = bytes0[int(offs0[qn]): int(offs0[qn + 1])]
+            m = pat.numel()
+            hit = text[: n - m + 1] == pat[0]
+            for k in range(1, m):
+                hit &= text[k: n - m + 1 + k] == pat[k]
+            naive_ok = naive_ok and int(hit.sum()) == int(c0[qn])
+            del hit
+    except Exception as e:  # pragma: no cover
+        naive_ok = f"unavailable: {e!r}"
 
+    e2e = {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "api": "csfm_count_batch_submit_len8/_wait (host pointers, pinned, one length byte per pattern in, u32 counts "
+                  "out, 3 steps in flight)",
+           "kernels_per_step": 4}
+    if copy_s:
+        ceil_v = world * e2e_steps * batch / copy_s
+        e2e["copy_ceiling"] = {"value": ceil_v, "unit": "queries/s", "ms_per_step": 1e3 * copy_s / e2e_steps,
+                               "h2d_gbs_per_gpu": h2d * e2e_steps / copy_s / 1e9, "d2h_gbs_per_gpu": d2h * e2e_steps / copy_s / 1e9,
+                               "note": "the same H2D + D2H bytes per step from/to pinned memory, three streams per rank like the "
+                                       "product's three slots, every rank at once, no kernel: what the host<->device links of this box "
+                                       "allow at this N"}
+        e2e["frac_of_copy_ceiling"] = e2e_value / ceil_v
+    if full:
+        e2e.update({
+            "u32_api": {"value": world * e2e_steps * batch / e2e_s_u32, "ms_per_step": 1e3 * e2e_s_u32 / e2e_steps,
+                        "h2d_bytes_per_step": e2e_bytes["u32"][0], "d2h_bytes_per_step": e2e_bytes["u32"][1],
+                        "api": "csfm_count_batch_submit32/_wait (u32 offsets and counts)"},
+            "u64_api": {"value": world * e2e_steps * batch / e2e_s_u64, "ms_per_step": 1e3 * e2e_s_u64 / e2e_steps,
+                        "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
+                        "api": "csfm_count_batch_submit/_wait (u64 offsets and counts)"},
+            "sync_call_ms_per_step": e2e_sync_ms, "sync_call_value": world * batch / (e2e_sync_ms / 1e3)})
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -893,31 +1052,209 @@ def run_engine(args, rank, world, local_rank):
         "config": {"workload": wl["desc"], "n": n, "levels": L, "line_bytes": int(info.line_bytes), "layout": int(info.layout),
                    "sigma": int(info.sigma), "batch_per_gpu": batch,
                    "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
-                   "l2_policy": f"inputs larger than L2: {info.blob_bytes / 1e9:.2f} GB index + a different 28 MB batch every step" if n >= (1 << 29)
-                   else "index is L2-resident at this size; a different batch every step",
-                   "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": args.n_log2 in (None, wl["n_log2"]),
+                   "l2_policy": f"inputs larger than L2: {info.blob_bytes / 1e9:.2f} GB index + a different batch every step" if not in_l2
+                   else f"index ({info.blob_bytes / 1e6:.0f} MB) is L2-resident at this size; a different batch every step",
+                   "index_build_s": build_s, "index_broadcast_ms": bcast_ms, "full_size": n == wl.get("n", 1 << wl["n_log2"]),
                    "build_flags": "CSFM_BUILD_LARGE_TABLE" if args.large_table else "default"},
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": "csfm_count_batch_submit_len8/_wait (host pointers, pinned, one length byte per pattern in, u32 counts "
-                       "out, 3 steps in flight)",
-                "kernels_per_step": 4,
-                "u32_api": {"value": world * e2e_steps * batch / e2e_s_u32, "ms_per_step": 1e3 * e2e_s_u32 / e2e_steps,
-                            "h2d_bytes_per_step": e2e_bytes["u32"][0], "d2h_bytes_per_step": e2e_bytes["u32"][1],
-                            "api": "csfm_count_batch_submit32/_wait (u32 offsets and counts)"},
-                "u64_api": {"value": world * e2e_steps * batch / e2e_s_u64, "ms_per_step": 1e3 * e2e_s_u64 / e2e_steps,
-                            "h2d_bytes_per_step": h2d64, "d2h_bytes_per_step": d2h64,
-                            "api": "csfm_count_batch_submit/_wait (u64 offsets and counts)"},
-                "sync_call_ms_per_step": e2e_sync_ms, "sync_call_value": world * batch / (e2e_sync_ms / 1e3)},
+        "e2e": e2e,
         "gpu_launches": args.steps,  # the timed region of `value`: one count kernel per step
-        "gpu_launches_all_timed_legs": launches + e2e_steps * (1 + 3 + 4),  # + stepping-only, large-table, e2e forms (u64 1, u32 3, len8 4 kernels per step)
+        "gpu_launches_all_timed_legs": launches + e2e_steps * ((1 + 3 + 4) if full else 4),  # + stepping-only, large-table, e2e forms (u64 1, u32 3, len8 4 kernels per step)
         "roofline": roofline,
         "cpu_baseline": cpu,
         "construction": construction,
         "clocks": clocks.summary(),
-        "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal, "compact_equals_u64_api": compact_equal},
-        "locate": locate,
+        "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal, "compact_equals_u64_api": compact_equal,
+                   "naive_text_scan_equals_counts": naive_ok,
+                   "bit_exact_vs_reference_sample": (cpu or {}).get("bit_exact_vs_gpu")},
     }
+    idx.close()
+    del d_batches, h_batches, text
+    torch.cuda.empty_cache()
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[0]: the reference's own tools/benchmark.cpp workload (100 KB text, single queries)
+# ------------------------------------------------------------------------------------------------
+PUBLISHED_C1 = {"random_count_qps": 41530, "frequent_count_qps": 82803, "locate_qps": 8, "build_ms": 4400,
+                "source": "reference README.md:135-140 (unspecified Windows x64 host, MSVC Release, 1 thread)"}
+
+
+def leg_c1(local_rank, cpu_budget):
+    """BASELINE.json configs[0]. (a) the reference's tools/benchmark.cpp, compiled UNMODIFIED against the drop-in
+    cs::FMIndex (build/ref_callers/bin/benchmark): its own QPS / latency lines, every query one C-ABI call on the
+    GPU; (b) the same lists through count_batch / locate_batch (cs_benchmark_batch --batch); (c) the unmodified
+    reference on one host core over the same lists. Pattern lists and checksums: tests/golden/c1_workload.npz
+    (generated from the compiled reference by tests/golden/make_golden.py)."""
+    import re
+    import subprocess
+    import tempfile
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c1_workload.npz"))
+    text = z["text"]
+    rand = [text[p:p + 5].tobytes() for p in z["rand_pos"]]
+    freq10 = [bytes(p)[:l] for p, l in zip(z["freq_patterns"], z["freq_len"])]
+    freq = [freq10[i % 10] for i in range(10000)]
+    want = {"random": 9907582, "frequent": 16309000, "locate": 163090}
+    env = dict(os.environ, CS_DEVICE=str(local_rank))
+    out = {"workload": "C1: tools/benchmark.cpp — 100 001-byte text, 10 000 random len-5 + 10 000 frequent count() queries, "
+                       "100 locate() queries, one query per call", "published": PUBLISHED_C1}
+
+    def pat_file(d, name, pats):
+        path = os.path.join(d, name)
+        with open(path, "wb") as f:
+            f.write(struct.pack("<I", len(pats)))
+            for q in pats:
+                f.write(struct.pack("<I", len(q)))
+                f.write(q)
+        return path
+
+    # (a) the reference's benchmark binary on the drop-in
+    exe = os.path.join(ROOT, "build", "ref_callers", "bin", "benchmark")
+    if os.path.exists(exe):
+        try:
+            r = subprocess.run([exe], capture_output=True, text=True, errors="replace", timeout=300, env=env)
+            txt = r.stdout
+            blocks = re.split(r"\n\s*(Random patterns|Frequent patterns|Locate \(locate\)):\n", txt)
+            res = {}
+            for i in range(1, len(blocks) - 1, 2):
+                body = blocks[i + 1]
+                g = lambda pat: float(re.search(pat, body).group(1))
+                res[blocks[i]] = {"qps": g(r"Throughput:\s+([0-9.]+) QPS"), "p50_us": g(r"Latency p50:\s+([0-9.]+)"),
+                                  "p95_us": g(r"Latency p95:\s+([0-9.]+)"), "p99_us": g(r"Latency p99:\s+([0-9.]+)"),
+                                  "total_matches": int(g(r"Total matches:\s+([0-9]+)"))}
+            bm = re.search(r"Build time:\s+([0-9.]+) ms", txt)
+            out["rehosted_benchmark"] = {
+                "binary": "build/ref_callers/bin/benchmark (reference tools/benchmark.cpp, unmodified, linked against libcs_b200.so)",
+                "random_count": res.get("Random patterns"), "frequent_count": res.get("Frequent patterns"),
+                "locate": res.get("Locate (locate)"), "build_ms": float(bm.group(1)) if bm else None,
+                "total_matches_equal_reference": bool(res and res["Random patterns"]["total_matches"] == want["random"] and
+                                                      res["Frequent patterns"]["total_matches"] == want["frequent"] and
+                                                      res["Locate (locate)"]["total_matches"] == want["locate"]),
+                "note": "build_ms includes creating the CUDA context (first call of the process)"}
+        except Exception as e:  # pragma: no cover
+            out["rehosted_benchmark"] = {"unavailable": repr(e)}
+    else:
+        out["rehosted_benchmark"] = {"unavailable": "build/ref_callers/bin/benchmark not built"}
+
+    # (b) single-query loops and the batch entry points of the drop-in class on the same lists
+    tool = os.path.join(ROOT, "compressed-fm-index-implementation-with-learned-optimizations_b200", "host", "cs_benchmark_batch")
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            tpath = os.path.join(d, "text.bin")
+            text.tofile(tpath)
+            runs = {}
+            for name, cp in (("random", rand), ("frequent", freq)):
+                r = subprocess.run([tool, tpath, pat_file(d, name + ".pat", cp), pat_file(d, "loc.pat", freq[:100]), "--batch"],
+                                   capture_output=True, text=True, timeout=300, env=env)
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr[-400:])
+                runs[name] = json.loads(r.stdout)
+        out["dropin_class"] = {
+            "binary": "host/cs_benchmark_batch (host/tools/benchmark_batch.cpp: cs::FMIndex::count / locate per pattern, then count_batch / locate_batch)",
+            "build_ms": runs["random"]["build_ms"],
+            "random_count_single": runs["random"]["count_single"], "frequent_count_single": runs["frequent"]["count_single"],
+            "locate_single": runs["random"]["locate_single"],
+            "random_count_batch": runs["random"]["count_batch"], "frequent_count_batch": runs["frequent"]["count_batch"],
+            "locate_batch": runs["random"]["locate_batch"],
+            "total_matches_equal_reference": bool(runs["random"]["count_single"]["total_matches"] == want["random"] and
+                                                  runs["random"]["count_batch"]["total_matches"] == want["random"] and
+                                                  runs["frequent"]["count_batch"]["total_matches"] == want["frequent"] and
+                                                  runs["random"]["locate_single"]["total_matches"] == want["locate"] and
+                                                  runs["random"]["locate_batch"]["occurrences"] == want["locate"])}
+        rs = runs["random"]["count_single"]
+        out["value"] = rs["qps"]
+        out["unit"] = "count queries/s, one query per call (random len-5 list)"
+        out["vs_published"] = {"random_count": rs["qps"] / PUBLISHED_C1["random_count_qps"],
+                               "frequent_count": runs["frequent"]["count_single"]["qps"] / PUBLISHED_C1["frequent_count_qps"],
+                               "locate": runs["random"]["locate_single"]["qps"] / PUBLISHED_C1["locate_qps"]}
+    except Exception as e:  # pragma: no cover
+        out["dropin_class"] = {"unavailable": repr(e)}
+    out["roofline"] = {"bound": "launch latency", "achieved": None, "peak": None, "frac": None, "unit": "us",
+                       "note": "a single query is ONE kernel launch (pattern in the kernel parameters, result through mapped pinned "
+                               "memory the host spins on) of one warp walking ~6 dependent L2 hits: p50 is launch + PCIe round trip, "
+                               "not memory bandwidth; the 0.1 MB index lives in L2. The batch calls move 10 000 queries in one launch"}
+
+    # (c) the unmodified reference on this host, one thread, same lists
+    if cpu_budget > 0:
+        try:
+            import oracle
+            ref = oracle.RefIndex(text.tobytes(), stride=32, sa=z["sa"])
+            base = {}
+            for name, cp in (("random", rand), ("frequent", freq)):
+                data, offs = oracle.pack_patterns(cp)
+                t0 = time.perf_counter()
+                c = ref.count_batch(data, offs, nthreads=1)
+                dt = time.perf_counter() - t0
+                base[name + "_count_qps"] = len(cp) / dt
+                base[name + "_total_matches_ok"] = int(c.sum()) == want[name]
+            data, offs = oracle.pack_patterns(freq[:20])
+            t0 = time.perf_counter()
+            tot, _, _ = ref.locate_batch(data, offs, limit=100000, nthreads=1)
+            dt = time.perf_counter() - t0
+            base["locate_qps"] = 20 / dt
+            base["locate_occ_per_s"] = tot / dt
+            out["cpu_baseline"] = {"value": base["random_count_qps"], "unit": "queries/s", "cores": 1, "kind": "reference",
+                                   "sample": "full 10 000-query lists for count, 20 of the 100 locate queries, verbatim cs::FMIndex "
+                                             "(oracle/_ref) on one host thread like the reference's tool", **base}
+        except Exception as e:  # pragma: no cover
+            out["cpu_baseline"] = {"value": None, "kind": "reference", "sample": f"unavailable: {e!r}"}
+    return out
+
+
+def run_engine(args, rank, world, local_rank):
+    """The headline line (the workload named by --workload, default c3 = configs[2]) plus, by default, one leg per
+    other BASELINE.json config under `configs`: c1 (rank 0), c2, c4 (= `locate`), c5 — every rank takes part in
+    the count / locate legs (weak scaling), rank 0 prints."""
+    import torch
+    import csfm_b200 as fm
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    t_start = time.perf_counter()
+    line = count_leg(args, args.workload, rank, world, local_rank, args.steps, args.warmup, full=True)
+    legs_s = {"main": time.perf_counter() - t_start}
+    cpu_ok = not (args.no_cpu_baseline or world > 1)
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            return fn()
+        except Exception as e:  # pragma: no cover
+            if world > 1:
+                raise  # a rank that drops out of the collectives would hang the others
+            return {"unavailable": repr(e)}
+        finally:
+            torch.cuda.empty_cache()
+            legs_s[name] = time.perf_counter() - t0
+
+    locate = None
+    if not args.no_locate:
+        locate = guarded("c4", lambda: measure_locate(fm, dev, rank, world, npat=args.locate_patterns,
+                                                     cpu_budget=min(args.cpu_budget, 10.0) if cpu_ok else 0.0))
+    configs = {}
+    if not args.no_configs and args.workload == "c3" and args.n_log2 is None:
+        sub = argparse.Namespace(**vars(args))
+        sub.no_cpu_baseline = not cpu_ok
+        sub.n_log2 = None
+        sub.large_table = False
+        c2 = guarded("c2", lambda: count_leg(sub, "c2", rank, world, local_rank, min(args.steps, 100), 5, full=False))
+        if rank == 0:
+            configs["c1"] = guarded("c1", lambda: leg_c1(local_rank, args.cpu_budget if cpu_ok else 0.0))
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        free_gb = torch.cuda.mem_get_info()[0] / 1e9
+        if free_gb > 150:
+            c5_steps = max(3, -(-100 // world))  # the 100 M-pattern sweep of the config, split over the ranks
+            c5 = guarded("c5", lambda: count_leg(sub, "c5", rank, world, local_rank, c5_steps, 3, full=False))
+        else:
+            c5 = {"unavailable": f"needs > 150 GB of free device memory for the 4e9-byte build, {free_gb:.0f} GB free"}
+        configs.update({"c2": c2, "c4": "see `locate`", "c5": c5})
+    if rank != 0:
+        return
+    line["locate"] = locate
+    if configs:
+        line["configs"] = configs
+    line["legs_wall_s"] = legs_s
     emit(line)
 
 
@@ -935,7 +1272,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--large-table", action="store_true", help="build the MAIN index with CSFM_BUILD_LARGE_TABLE (opt-in mode)")
     ap.add_argument("--no-large-table", action="store_true", help="skip the leg on an index with a 34 GB k-mer table")
-    ap.add_argument("--no-locate", action="store_true", help="skip the locate leg (occurrences/s on a C4-style index)")
+    ap.add_argument("--no-locate", action="store_true", help="skip the locate leg (configs[3]: occurrences/s)")
+    ap.add_argument("--locate-patterns", type=int, default=1_000_000, help="patterns per GPU in the locate leg (configs[3]: 1 M)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configs (c1, c2, c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

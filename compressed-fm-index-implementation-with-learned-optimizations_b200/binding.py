@@ -55,7 +55,8 @@ class IndexInfo(C.Structure):
 class CallStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("search_steps", C.c_uint64), ("lf_steps", C.c_uint64), ("kernel_ms", C.c_float),
-                ("table_lookups", C.c_uint32), ("text_checks", C.c_uint32), ("half_steps", C.c_uint32)]
+                ("table_lookups", C.c_uint32), ("text_checks", C.c_uint32), ("half_steps", C.c_uint32), ("pad0", C.c_uint32),
+                ("line_fetches", C.c_uint64)]
 
 
 # name -> (restype, argtypes): every symbol include/csfm.h declares

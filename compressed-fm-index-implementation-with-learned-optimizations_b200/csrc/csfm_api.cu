@@ -440,6 +440,7 @@ static int end_call(csfm_index* idx, cudaStream_t stream, bool locate) {
       idx->stats.table_lookups = (uint32_t)hp[10];
       idx->stats.text_checks = (uint32_t)hp[11];
       idx->stats.half_steps = (uint32_t)hp[12];
+      idx->stats.line_fetches = hp[13];
     }
   }
   if (idx->instr_mask & 2u) {
@@ -848,6 +849,7 @@ int csfm_last_call_stats(const csfm_index* idx, csfm_call_stats* out) {
     if (!out->table_lookups) out->table_lookups = (uint32_t)hp[10];
     if (!out->text_checks) out->text_checks = (uint32_t)hp[11];
     if (!out->half_steps) out->half_steps = (uint32_t)hp[12];
+    if (!out->line_fetches) out->line_fetches = hp[13];
     if (!out->lf_steps) out->lf_steps = hp[9];
   }
   if ((idx->instr_mask & 2u) && out->kernel_ms == 0.f) {

@@ -356,7 +356,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   idx->stats.kernel_launches += 1;
   if (a.steps_total) {  // ctr[1] = rank steps, ctr[2] = k-mer table lookups
     CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 8, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
-    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 10, ctr + 2, 24, cudaMemcpyDeviceToHost, stream));  // + ctr[4] = half steps
+    CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 10, ctr + 2, 32, cudaMemcpyDeviceToHost, stream));  // + ctr[4] = half steps, ctr[5] = level lines fetched
   }
   return CSFM_OK;
 }

@@ -102,7 +102,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   uint32_t rem = 0;              // characters left including the current one
   uint32_t sp = 0, ep = 0, base = 0, add0 = 0, code = 0, next_byte = 0;
   uint32_t vstage = 0, vp = 0;   // 0 searching, 1 suffix-array entry requested, 2 windows in flight
-  uint32_t my_steps = 0, my_lookups = 0, my_checks = 0, my_halves = 0;
+  uint32_t my_steps = 0, my_lookups = 0, my_checks = 0, my_halves = 0, my_lines = 0;
   uint32_t since_refill = 0;     // warp-uniform: trips since this warp last took queries
   bool pre = false;              // sp/ep already hold the level-1 interval of the pending step (half-step table)
   const uint2* const kmer_hi = kShortcut ? iv.kmer_hi : nullptr;  // the plain variant stays within 32 registers
@@ -293,12 +293,14 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (kShortcut && !__any_sync(0xFFFFFFFFu, ranking)) continue;  // a trip of verifications only
     uint32_t rs, re, s1 = sp, e1 = ep;  // sp and ep themselves must survive a trip spent in verification
     if (two && (!kShortcut || __any_sync(0xFFFFFFFFu, ranking && !pre))) {
+      if (kInstr && ranking && !pre) my_lines += 1u + (((sp ^ ep) >> 7) != 0u);
       rank_pair(lv0, code >> 4, sp, ep, ranking && !pre, j, rs, re);
       if (!pre) {
         s1 = add0 + rs;
         e1 = add0 + re;
       }
     }
+    if (kInstr && ranking) my_lines += 1u + (((s1 ^ e1) >> 7) != 0u);
     rank_pair(lv_last, code & 15u, s1, e1, ranking, j, rs, re);
     if (ranking) {
       pre = false;
@@ -323,13 +325,15 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   }
   if (kInstr && a.steps_total) {
     unsigned s = (j == 0) ? my_steps : 0, t = (j == 0) ? my_lookups : 0, u = (j == 0) ? my_checks : 0,
-             v = (j == 0) ? my_halves : 0;
+             v = (j == 0) ? my_halves : 0, w = (j == 0) ? my_lines : 0;
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
       t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
       u += __shfl_xor_sync(0xFFFFFFFFu, u, o);
       v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
     }
+    if (lane == 0 && w) atomicAdd(a.steps_total + 4, (unsigned long long)w);
     if (lane == 0 && s) atomicAdd(a.steps_total, (unsigned long long)s);
     if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
     if (lane == 0 && u) atomicAdd(a.steps_total + 2, (unsigned long long)u);

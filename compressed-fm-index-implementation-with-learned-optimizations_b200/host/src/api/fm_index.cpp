@@ -2,6 +2,7 @@
 // Mirrors the behaviour of /root/reference/src/api/fm_index.cpp; contains no FM-index algorithm.
 #include "fm_index.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <exception>
@@ -152,16 +153,21 @@ LocateBatch FMIndex::locate_batch(const std::vector<std::string_view>& patterns,
   std::vector<uint8_t> bytes;
   std::vector<uint64_t> offs;
   pack(patterns, bytes, offs);
+  // One pass when the guess holds: positions land in a buffer sized from the previous call on this index (a
+  // single pattern sizes first: the library remembers its interval, so the second call only walks).
   uint64_t total = 0;
-  int rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(), nullptr,
-                             0, r.status.data(), &total);
-  if (rc != CSFM_OK) throw_last("locate_batch");
-  r.positions.resize(total);
-  if (total) {
+  uint64_t cap = patterns.size() == 1 ? 0 : std::max<uint64_t>(*locate_hint_, 64 * patterns.size());
+  r.positions.resize(cap);
+  int rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
+                             cap ? r.positions.data() : nullptr, cap, r.status.data(), &total);
+  if (rc == CSFM_ERR_CAPACITY || (rc == CSFM_OK && cap == 0 && total != 0)) {
+    r.positions.resize(total);
     rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
                            r.positions.data(), total, r.status.data(), &total);
-    if (rc != CSFM_OK) throw_last("locate_batch");
   }
+  if (rc != CSFM_OK) throw_last("locate_batch");
+  r.positions.resize(total);
+  if (patterns.size() > 1) *locate_hint_ = total + total / 8;
   return r;
 }
 

@@ -85,6 +85,7 @@ private:
   IndexMeta meta_;
   std::shared_ptr<const std::string> text_;  // host copy for extract(), like FMIndex::text_
   std::shared_ptr<csfm_index> handle_;       // device-resident index; copies share it (read-only)
+  std::shared_ptr<uint64_t> locate_hint_ = std::make_shared<uint64_t>(0);  // positions of the previous locate_batch: sizes the next one
 };
 
 }  // namespace cs

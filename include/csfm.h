@@ -127,6 +127,9 @@ typedef struct {
                                text (those characters are not in search_steps); 0 unless asked */
   uint32_t half_steps;      /* first steps taken from the half-step table: one level (2 lines) instead
                                of two; not in search_steps; 0 unless asked */
+  uint32_t pad0;
+  uint64_t line_fetches;    /* level lines the rank steps of the call actually loaded (sp and ep share one
+                               load when they fall in the same line); layout 2 count kernels; 0 unless asked */
 } csfm_call_stats;
 
 CSFM_API const char* csfm_last_error(void);
