@@ -24,6 +24,7 @@ CSFM_OK, CSFM_ERR_INVALID, CSFM_ERR_CUDA, CSFM_ERR_NOMEM, CSFM_ERR_TOO_LARGE, CS
 Q_OK, Q_LF_WALK_EXCEEDED, Q_SSA_OOB = 0, 1, 2
 BUILD_DEFAULT, BUILD_NO_COMPACT, BUILD_KEEP_SA, BUILD_LAYOUT_BINARY64, BUILD_NO_KMER_TABLE, BUILD_NO_TEXT_CHECK, BUILD_FORCE_TEXT_CHECK = 0, 1, 2, 4, 8, 16, 32
 BUILD_LARGE_TABLE = 64
+BUILD_LAYOUT_NIBBLE128 = 128
 
 LF_WALK_MESSAGE = "locate: LF walk exceeded text length"  # fm_index.cpp:137
 

@@ -4,7 +4,7 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="${CSFM_OUT:-$HERE/libcsfm.so}"  # CSFM_OUT / CSFM_NVCC_EXTRA: experiment builds beside the product library
-SRCS=("$HERE"/csrc/csfm_api.cu "$HERE"/csrc/csfm_build.cu "$HERE"/csrc/csfm_query.cu "$HERE"/csrc/csfm_query2.cu "$HERE"/csrc/csfm_sa.cu)
+SRCS=("$HERE"/csrc/csfm_api.cu "$HERE"/csrc/csfm_build.cu "$HERE"/csrc/csfm_query.cu "$HERE"/csrc/csfm_query2.cu "$HERE"/csrc/csfm_query3.cu "$HERE"/csrc/csfm_sa.cu)
 newest=$(ls -t "$HERE"/csrc/* "$HERE"/../include/csfm.h "$HERE"/build.sh | head -1)
 if [[ -f "$OUT" && "$OUT" -nt "$newest" && "${1:-}" != "-f" ]]; then
   exit 0

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "csfm_dna.cuh"
 #include "csfm_host.hpp"
 #include "csfm_kernels.cuh"
 
@@ -216,7 +217,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->blob_bytes = idx->blob_bytes;
   out->has_sa = idx->d_sa != nullptr;
   out->layout = idx->h.layout;
-  out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;
+  out->line_bytes = idx->h.layout == kLayoutNibble128 ? kLine2Bytes : kLineBytes;  // layouts 1 and 3: 64-byte lines
   out->kmer_k = idx->view.kmer_k;
   out->text_check = idx->view.text != nullptr;
   out->half_table = idx->view.kmer_hi != nullptr;
@@ -296,9 +297,10 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   CSFM_CUDA(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost));
   if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 3) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
   const bool nib = h.layout == kLayoutNibble128;
-  const uint64_t per_line = nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
-  if ((h.layout != kLayoutNibble128 && h.layout != kLayoutBinary64) || h.total_bytes > bytes || h.levels == 0 ||
-      h.levels > (nib ? 2u : kMaxLevels) || h.nblk != h.n / per_line + 1 || h.off_levels < sizeof(BlobHeader) ||
+  const bool dna = h.layout == kLayoutDna64;
+  const uint64_t per_line = dna ? kSymsPerLine3 : nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
+  if ((h.layout != kLayoutNibble128 && h.layout != kLayoutBinary64 && h.layout != kLayoutDna64) || h.total_bytes > bytes || h.levels == 0 ||
+      h.levels > (nib ? 2u : dna ? 1u : kMaxLevels) || h.nblk != h.n / per_line + 1 || h.off_levels < sizeof(BlobHeader) ||
       h.off_ssa + h.nsamp * 4 > h.total_bytes || h.stride == 0 ||
       h.off_levels + (uint64_t)h.levels * h.level_stride > h.off_ssa || h.level_stride < h.nblk * line_bytes ||
       h.nsamp != (h.n + h.stride - 1) / h.stride)
@@ -312,7 +314,7 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
     uint64_t entries = 1;
     for (uint32_t i = 0; i < h.kmer_k && entries <= (1ull << 40); ++i) entries *= h.kmer_radix;
     const uint64_t table_bytes = h.kmer_tiled ? (entries + 1) * 4 : entries * 8;
-    if (!nib || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
+    if (!(nib || dna) || (dna && (h.kmer_tiled || h.off_kmer_hi)) || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
         h.kmer_tiled > 1 || (h.kmer_tiled && !h.off_text) || h.off_kmer + table_bytes > h.total_bytes)
       return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
     if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + table_bytes || h.off_kmer_hi + entries * 128 > h.total_bytes))
@@ -334,7 +336,10 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
         ++present;
         if (nib && (h.code_of_byte[c] >> 4) >= (h.levels == 2 ? 16u : 1u))
           return fail(CSFM_ERR_FORMAT, "blob header: compact code does not fit the level count");
-        if (!nib && h.levels < 8 && (h.code_of_byte[c] >> h.levels) != 0)
+        if (dna && h.code_of_byte[c] > kSpecialCode) return fail(CSFM_ERR_FORMAT, "blob header: code beyond the two-bit alphabet");
+        if (dna && h.code_of_byte[c] == kSpecialCode && (h.C[c + 1] - h.C[c] != 1 || h.special_byte != (uint32_t)c || h.special_row >= h.n))
+          return fail(CSFM_ERR_FORMAT, "blob header: inconsistent single-occurrence symbol");
+        if (!nib && !dna && h.levels < 8 && (h.code_of_byte[c] >> h.levels) != 0)
           return fail(CSFM_ERR_FORMAT, "blob header: compact code does not fit the level count");
       }
     }
@@ -342,10 +347,11 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
     for (int g = 0; g < 16; ++g)
       if (h.start1[g] > h.n || (g && h.start1[g] < h.start1[g - 1]))
         return fail(CSFM_ERR_FORMAT, "blob header: start1 not monotone within [0, n]");
-    if (!nib)
+    if (dna && (h.off_text || h.sigma > 5)) return fail(CSFM_ERR_FORMAT, "blob header: layout 3 with text sections or more than five symbols");
+    if (!nib && !dna)
       for (uint32_t l = 0; l < h.levels; ++l)
         if (h.zeros[l] > h.n) return fail(CSFM_ERR_FORMAT, "blob header: zeros[] beyond n");
-    if (h.kmer_k && h.kmer_radix != h.sigma && h.kmer_radix != 256)
+    if (h.kmer_k && h.kmer_radix != (dna ? std::min<uint32_t>(h.sigma, 4u) : h.sigma) && (dna || h.kmer_radix != 256))
       return fail(CSFM_ERR_FORMAT, "blob header: k-mer radix differs from the alphabet");
     if (h.off_text && h.dense_shift != 0) return fail(CSFM_ERR_FORMAT, "blob header: text sections need the full suffix array");
     if (h.verify_min > 64) return fail(CSFM_ERR_FORMAT, "blob header: verify_min out of range");

@@ -21,6 +21,7 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include "csfm_dna.cuh"
 #include "csfm_host.hpp"
 
 namespace csfm {
@@ -208,6 +209,60 @@ nib_split_kernel(const uint8_t* __restrict__ cur, uint8_t* __restrict__ nxt, uin
   }
 }
 
+// ---- layout 3 (csfm_dna.cuh) --------------------------------------------------------------
+// u32 index inside a 64-byte line of pair t (0..5) / counter v (0..3): lane h = t / 3 holds pairs 3h..3h+2
+__device__ __forceinline__ uint32_t dna_word_of_pair(uint32_t t) { return 8u * (t / 3u) + 2u + 2u * (t % 3u); }
+__device__ __forceinline__ uint32_t dna_word_of_counter(uint32_t v) { return 8u * (v >> 1) + (v & 1u); }
+
+// One warp per line: the six (lo, hi) pairs + the per-line histogram linecnt[v * nblk + b]. `cur` holds compact
+// codes; the symbol that occurs once (code 4) is stored and counted as a 0.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+dna_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, uint8_t* __restrict__ level, uint64_t nblk,
+                uint32_t* __restrict__ linecnt) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t b = warp; b < nblk; b += nwarps) {
+    uint32_t* line = reinterpret_cast<uint32_t*>(level + b * kLine3Bytes);
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 6; ++t) {
+      const uint64_t i = b * kSymsPerLine3 + 32 * t + lane;
+      const bool valid = i < n;
+      uint32_t v = valid ? cur[i] : 0u;
+      if (v >= 4u) v = 0u;
+      const uint32_t lo = __ballot_sync(0xFFFFFFFFu, v & 1u), hi = __ballot_sync(0xFFFFFFFFu, v & 2u);
+      const uint32_t in = __ballot_sync(0xFFFFFFFFu, valid);
+      c0 += __popc(~lo & ~hi & in);
+      c1 += __popc(lo & ~hi & in);
+      c2 += __popc(~lo & hi & in);
+      c3 += __popc(lo & hi & in);
+      if (lane == 0) {
+        line[dna_word_of_pair(t)] = lo;
+        line[dna_word_of_pair(t) + 1] = hi;
+      }
+    }
+    if (lane < 4) linecnt[(uint64_t)lane * nblk + b] = lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
+  }
+}
+
+__global__ void dna_counters_kernel(uint8_t* __restrict__ level, uint64_t nblk, const uint32_t* __restrict__ prefix) {
+  const uint64_t total = nblk * 4;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const uint64_t b = t >> 2;
+    const uint32_t v = (uint32_t)(t & 3);
+    reinterpret_cast<uint32_t*>(level + b * kLine3Bytes)[dna_word_of_counter(v)] = prefix[(uint64_t)v * nblk + b];
+  }
+}
+
+// row of the one occurrence of `byte` in the BWT
+__global__ void find_byte_kernel(const uint8_t* __restrict__ data, uint64_t n, uint8_t byte, unsigned int* __restrict__ row) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (data[i] == byte) *row = (unsigned int)i;
+}
+
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 uint32_t bit_reverse(uint32_t v, int bits) {
@@ -258,6 +313,30 @@ static void fill_tables(BlobHeader& h, const unsigned long long hist[256], uint3
   std::memset(h.base_by_code, 0, sizeof h.base_by_code);
   std::memset(h.start1, 0, sizeof h.start1);
 
+  if (h.layout == kLayoutDna64) {
+    // up to four two-bit codes in byte order; with five symbols the one that occurs once (the smallest such
+    // byte) becomes kSpecialCode and has no slot in the lines
+    int special = -1;
+    if (sigma == 5)
+      for (int c = 0; c < 256 && special < 0; ++c)
+        if (hist[c] == 1) special = c;
+    std::memset(h.code_of_byte, 0, 256);
+    std::memset(h.byte_of_code, 0, 256);
+    uint32_t next = 0;
+    for (int c = 0; c < 256; ++c) {
+      if (!hist[c]) continue;
+      const uint32_t code = c == special ? kSpecialCode : next++;
+      h.code_of_byte[c] = (uint8_t)code;
+      h.byte_of_code[code] = (uint8_t)c;
+      h.base_by_byte[c] = h.C[c];  // one level: rank gives occ(c, .) itself
+      h.base_by_code[code] = h.C[c];
+    }
+    h.levels = 1;
+    h.code_bits = 2;
+    h.special_byte = special < 0 ? 0u : (uint32_t)special;
+    h.special_row = kNoSpecialRow;  // filled in once the BWT has been scanned
+    return;
+  }
   if (h.layout == kLayoutNibble128) {
     h.levels = B <= 4 ? 1 : 2;
     if (h.levels == 2) {
@@ -321,6 +400,9 @@ int index_finish_handle(csfm_index* idx) {
   v.stride_shift = 32;
   if ((h.stride & (h.stride - 1)) == 0)
     for (v.stride_shift = 0; (1u << v.stride_shift) < h.stride; ++v.stride_shift) {}
+  v.special_row = h.layout == kLayoutDna64 ? h.special_row : kNoSpecialRow;
+  v.special_byte = h.special_byte;
+  v.special_first = h.C[h.special_byte & 0xFFu];
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
@@ -387,12 +469,28 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   h.stride = stride;
   h.nsamp = nsamp;
   h.layout = (flags & CSFM_BUILD_LAYOUT_BINARY64) ? kLayoutBinary64 : kLayoutNibble128;
+  h.special_row = kNoSpecialRow;
+  if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
+  {
+    // layout 3 (two-bit symbols, 64-byte lines) whenever the text allows it: at most four symbols, or five of
+    // which one occurs exactly once; the text-verification sections and raw byte codes exist in layout 2 only
+    uint32_t present = 0, singles = 0;
+    for (int c = 0; c < 256; ++c) {
+      present += hist[c] != 0;
+      singles += hist[c] == 1;
+    }
+    const uint32_t keep2 = CSFM_BUILD_LAYOUT_BINARY64 | CSFM_BUILD_NO_COMPACT | CSFM_BUILD_LAYOUT_NIBBLE128 |
+                           CSFM_BUILD_FORCE_TEXT_CHECK | CSFM_BUILD_LARGE_TABLE;
+    if (!(flags & keep2) && n > 0 && (present <= 4 || (present == 5 && singles >= 1)) && !std::getenv("CSFM_NO_DNA_LAYOUT"))
+      h.layout = kLayoutDna64;
+  }
   fill_tables(h, hist, flags);
   const uint32_t L = h.levels;
   const bool nib = h.layout == kLayoutNibble128;
-  h.nblk = nib ? n / kSymsPerLine + 1 : n / kPayloadBits + 1;
+  const bool dna = h.layout == kLayoutDna64;
+  h.nblk = dna ? n / kSymsPerLine3 + 1 : nib ? n / kSymsPerLine + 1 : n / kPayloadBits + 1;
   h.off_levels = kHeaderBytes;
-  h.level_stride = align_up(h.nblk * (nib ? kLine2Bytes : kLineBytes), 256);
+  h.level_stride = align_up(h.nblk * (nib ? kLine2Bytes : kLineBytes), 256);  // layouts 1 and 3: 64-byte lines
   h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
   h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
   // k-mer jump table: the first k steps of a query become one lookup. Budget: a quarter of the
@@ -400,7 +498,6 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   // 11 for DNA+$ at 4e9).
   // (decided first because it also selects the table format) Text sections: see below.
   const bool levels_in_hbm = (uint64_t)L * h.level_stride > (96ull << 20);
-  if (std::getenv("CSFM_FORCE_TEXT_CHECK")) flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
   if (flags & CSFM_BUILD_LARGE_TABLE) {
     // after a long key little is left to step through: verify from three characters on, whatever the level count
     flags |= CSFM_BUILD_FORCE_TEXT_CHECK;
@@ -413,12 +510,15 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
     const cudaError_t e2 = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost);
     text_sections = e2 == cudaSuccess && hist[last] == 1 && h.C[last] == 0;
   }
-  if (nib && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
+  if ((nib || dna) && n && !(flags & CSFM_BUILD_NO_KMER_TABLE)) {
     // with the text on board the table holds sp only (4 bytes per key) and is filled from the text's k-gram histogram
     const bool tiled = text_sections && !std::getenv("CSFM_BUILD_PAIR_TABLE");
     const uint64_t entry_bytes = tiled ? 4 : 8;
-    const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : h.sigma;
-    uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, (uint64_t)L * h.level_stride / 4));
+    // layout 3: keys are built from the two-bit codes only (a pattern that contains the symbol occurring once
+    // starts from the C array instead), so the table has 4^k entries, not 5^k
+    const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : dna ? std::min<uint64_t>(h.sigma, 4) : h.sigma;
+    // a quarter of a byte per text symbol (layout 2 on bytes <= 16 symbols: a quarter of the level bytes)
+    uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, dna ? n / 4 : (uint64_t)L * h.level_stride / 4));
     if (flags & CSFM_BUILD_LARGE_TABLE) {
       // opt-in: spend device memory on the table so that the lookup itself leaves few rows and the
       // query goes straight to the text verification (k = 4 for a byte alphabet at n = 2^30: 34 GB;
@@ -498,7 +598,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   } while (0)
 
   const uint64_t nbuf = n ? n : 1;
-  const uint64_t ncnt = h.nblk * (nib ? 16 : 1);  // per-line counters before / after the scan
+  const uint64_t ncnt = h.nblk * (nib ? 16 : dna ? 4 : 1);  // per-line counters before / after the scan
   BUILD_CUDA(cudaMalloc(&d_cur, nbuf));
   if (L > 1) BUILD_CUDA(cudaMalloc(&d_nxt, nbuf));
   BUILD_CUDA(cudaMalloc(&d_pop, ncnt * 4));
@@ -514,7 +614,21 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   const int wpb = kWarpsPerBlock;
   const uint64_t want_blocks = (h.nblk + wpb - 1) / wpb;
   const int grid = (int)std::min<uint64_t>(want_blocks, 148ull * 64);
-  if (nib) {
+  if (dna) {
+    uint8_t* level = idx->d_blob + h.off_levels;
+    dna_pack_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, level, h.nblk, d_pop);
+    for (int v = 0; v < 4; ++v)
+      BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop + (uint64_t)v * h.nblk,
+                                               d_rank + (uint64_t)v * h.nblk, (int64_t)h.nblk, st));
+    dna_counters_kernel<<<2048, 256, 0, st>>>(level, h.nblk, d_rank);
+    if (h.code_of_byte[h.special_byte & 0xFFu] == kSpecialCode) {
+      // the row of the symbol that occurs once (d_pop is free again: borrow its first word)
+      BUILD_CUDA(cudaMemsetAsync(d_pop, 0xFF, 4, st));
+      find_byte_kernel<<<1024, 256, 0, st>>>(d_bwt, n, (uint8_t)h.special_byte, d_pop);
+      BUILD_CUDA(cudaMemcpyAsync(&h.special_row, d_pop, 4, cudaMemcpyDeviceToHost, st));
+      BUILD_CUDA(cudaStreamSynchronize(st));
+    }
+  } else if (nib) {
     Start16 s16;
     std::memcpy(s16.s, h.start1, sizeof s16.s);
     for (uint32_t l = 0; l < L; ++l) {
@@ -567,7 +681,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   cleanup();
 #undef BUILD_CUDA
   int rc = index_finish_handle(idx);
-  if (rc == CSFM_OK && h.kmer_k) rc = build_kmer_table(idx, st);  // runs backward search over the finished levels
+  if (rc == CSFM_OK && h.kmer_k) rc = dna ? build_kmer_table3(idx, st) : build_kmer_table(idx, st);  // backward search over the finished levels
   if (rc != CSFM_OK) {
     csfm_destroy(idx);
     return rc;

@@ -40,6 +40,7 @@ namespace csfm {
 
 constexpr uint32_t kLayoutBinary64 = 1;
 constexpr uint32_t kLayoutNibble128 = 2;
+// kLayoutDna64 = 3: csfm_dna.cuh
 
 // layout 1
 constexpr uint32_t kPayloadBits = 480;  // bits per 64-byte line
@@ -93,7 +94,10 @@ struct BlobHeader {
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
-  uint32_t pad0[3];
+  // layout 3 (csfm_dna.cuh): BWT row of the symbol that occurs once (0xFFFFFFFF: the text has none) and its byte
+  uint32_t special_row;
+  uint32_t special_byte;
+  uint32_t pad0[1];
   uint32_t base_by_byte[256];  // see above (u32 wrap-around arithmetic)
   uint32_t base_by_code[256];  // same, indexed by compact code (LF step)
   uint8_t code_of_byte[256];   // compact code, 0 for absent bytes (absence <=> C[b+1]==C[b])
@@ -116,7 +120,7 @@ struct IndexView {
   uint32_t kmer_k;
   uint32_t kmer_radix;
   uint32_t kmer_tiled;  // table format, see BlobHeader
-  uint32_t pad0;
+  uint32_t special_row;  // layout 3: BWT row of the symbol that occurs once, 0xFFFFFFFF = none
   uint64_t level_stride;
   uint32_t n;
   uint32_t L;
@@ -128,6 +132,8 @@ struct IndexView {
   uint32_t verify_min;  // verify against the text only when at least this many characters are left
   uint32_t refill_min;   // shortcut kernel: a warp fetches new queries once this many of its sub-warps are idle ...
   uint32_t refill_wait;  // ... or this many trips after its last refill, whichever comes first
+  uint32_t special_first;  // layout 3: C[special byte] = the row LF maps special_row to
+  uint32_t special_byte;
   uint32_t zeros[kMaxLevels];
 };
 

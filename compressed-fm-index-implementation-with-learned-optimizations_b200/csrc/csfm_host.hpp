@@ -99,6 +99,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
                           const uint8_t* d_text = nullptr, const uint32_t* d_sa = nullptr);
 int index_finish_handle(csfm_index* idx);  // fills view/stream/workspace after d_blob + h are set
 int build_kmer_table(csfm_index* idx, cudaStream_t stream);  // csfm_query2.cu: fills the table sections
+int build_kmer_table3(csfm_index* idx, cudaStream_t stream);  // csfm_query3.cu: the same for layout 3
 // csfm_sa.cu
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,

@@ -116,6 +116,60 @@ __device__ __forceinline__ uint32_t queue_take32(WarpQueue32& q, bool need, int 
   return item;
 }
 
+// The same two queues for sub-warps of G lanes (G = 2: layout 3, sixteen queries per warp). The leader of a
+// sub-warp is its lowest lane; `need` must be uniform within a sub-warp.
+template <int G>
+__device__ __forceinline__ constexpr unsigned leader_mask() { return G == 1 ? 0xFFFFFFFFu : G == 2 ? 0x55555555u : G == 4 ? 0x11111111u : 0x01010101u; }
+
+template <int G>
+__device__ __forceinline__ uint32_t queue_take32g(WarpQueue32& q, bool need, int lane, unsigned long long* cursor, uint32_t total) {
+  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & leader_mask<G>();
+  if (need_mask == 0) return ~0u;
+  if (q.next >= q.end && !q.exhausted) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) {
+      q.exhausted = true;
+    } else {
+      q.next = (uint32_t)base;
+      q.end = (total - q.next > kChunk) ? q.next + kChunk : total;
+    }
+  }
+  const uint32_t avail = q.end - q.next;
+  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~(G - 1))) - 1u));
+  const unsigned cnt = __popc(need_mask);
+  uint32_t item = ~0u;
+  if (need && my_rank < avail) item = q.next + my_rank;
+  q.next += (cnt < avail) ? cnt : avail;
+  return item;
+}
+
+template <int G>
+__device__ __forceinline__ unsigned long long queue_takeg(WarpQueue& q, bool need, int lane, unsigned long long* cursor,
+                                                          unsigned long long total) {
+  const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need) & leader_mask<G>();
+  if (need_mask == 0) return ~0ull;
+  if (q.next >= q.end && !q.exhausted) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)kChunk);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= total) {
+      q.exhausted = true;
+    } else {
+      q.next = base;
+      q.end = (base + kChunk < total) ? base + kChunk : total;
+    }
+  }
+  const unsigned long long avail = q.end - q.next;
+  const unsigned my_rank = __popc(need_mask & ((1u << (lane & ~(G - 1))) - 1u));
+  const unsigned cnt = __popc(need_mask);
+  unsigned long long item = ~0ull;
+  if (need && my_rank < avail) item = q.next + my_rank;
+  q.next += (cnt < avail) ? cnt : avail;
+  return item;
+}
+
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX): pattern staging ------------------------
 // cp.async.bulk moves a contiguous, 16-byte aligned span global -> shared through the TMA unit
 // (SASS: UBLKCP) and signals an mbarrier with the byte count; nobody spends registers or issue
@@ -254,5 +308,12 @@ void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t st
 int max_blocks_per_sm_count2(bool tma_staging, const IndexView& iv, const CountArgs& a);
 int max_blocks_per_sm_walk2();
 int max_blocks_per_sm_access2();
+// Layout-3 kernels (csfm_query3.cu)
+void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream);
+void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
+void launch_access3(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
+int max_blocks_per_sm_count3(const CountArgs& a);
+int max_blocks_per_sm_walk3();
+int max_blocks_per_sm_access3();
 
 }  // namespace csfm

@@ -16,6 +16,7 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include "csfm_dna.cuh"
 #include "csfm_host.hpp"
 #include "csfm_kernels.cuh"
 
@@ -341,13 +342,17 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   a.cursor = ctr;
   a.steps_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
+  const bool dna = idx->view.layout == kLayoutDna64;
   const bool tma = idx->tma_staging;
-  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_count2(tma, idx->view, a) : persistent_grid(idx, (const void*)count_kernel);
-  const uint64_t want = (npat * 4 + kThreads - 1) / kThreads;
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_count3(a)
+                           : nib ? idx->num_sms * max_blocks_per_sm_count2(tma, idx->view, a) : persistent_grid(idx, (const void*)count_kernel);
+  const uint64_t want = (npat * (dna ? 2 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-  if (nib)
+  if (dna)
+    launch_count3(idx->view, a, grid, stream);
+  else if (nib)
     launch_count2(idx->view, a, grid, stream, tma);
   else
     count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
@@ -456,12 +461,16 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   w.cursor = ctr;
   w.lf_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
-  const int grid_max = nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
-  const uint64_t want = (count * 4 + kThreads - 1) / kThreads;
+  const bool dna = idx->view.layout == kLayoutDna64;
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_walk3()
+                           : nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
+  const uint64_t want = (count * (dna ? 2 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-  if (nib)
+  if (dna)
+    launch_walk3(idx->view, w, grid, stream);
+  else if (nib)
     launch_walk2(idx->view, w, grid, stream);
   else
     walk_kernel<<<grid, kThreads, 0, stream>>>(idx->view, w);
@@ -487,15 +496,20 @@ int offsets_from_lengths8(const uint8_t* d_lens, uint64_t count, uint64_t* d_off
 int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream) {
   if (idx->h.n == 0) return CSFM_OK;
   const bool nib = idx->view.layout == kLayoutNibble128;
+  const bool dna = idx->view.layout == kLayoutDna64;
   int per_sm = 0;
-  if (nib)
+  if (dna)
+    per_sm = max_blocks_per_sm_access3();
+  else if (nib)
     per_sm = max_blocks_per_sm_access2();
   else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, access_kernel, kThreads, 0);
   if (per_sm < 1) per_sm = 1;
   const uint64_t want = (idx->h.n * 4 + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)idx->num_sms * per_sm);
-  if (nib)
+  if (dna)
+    launch_access3(idx->view, d_out, grid, stream);
+  else if (nib)
     launch_access2(idx->view, d_out, grid, stream);
   else
     access_kernel<<<grid, kThreads, 0, stream>>>(idx->view, d_out);

@@ -87,6 +87,11 @@ typedef struct {
                                       straight to the text verification (implies CSFM_BUILD_FORCE_TEXT_CHECK):
                                       three dependent fetches per query. Same results, 1.5-1.9x the count
                                       throughput, an index of 10-25 GB */
+#define CSFM_BUILD_LAYOUT_NIBBLE128 128u /* keep layout 2 (16-ary levels, 128-byte lines) for a text that qualifies for
+                                           layout 3: two-bit symbols in 64-byte lines, one fetch per rank by a two-lane
+                                           sub-warp, chosen by default when the text has at most four distinct bytes, or
+                                           five of which one occurs exactly once (DNA + terminator): a third of the
+                                           bytes of layout 2, so configs[1] and configs[3] stay in the L2 */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
 
@@ -101,7 +106,7 @@ typedef struct {
   uint64_t blocks_per_level; /* 64-byte lines per level */
   uint64_t blob_bytes; /* size of the device-resident index */
   uint32_t has_sa;     /* full SA still resident (CSFM_BUILD_KEEP_SA) */
-  uint32_t layout;     /* 1 = binary / 64-byte lines, 2 = 16-ary / 128-byte lines */
+  uint32_t layout;     /* 1 = binary / 64-byte lines, 2 = 16-ary / 128-byte lines, 3 = two-bit symbols / 64-byte lines */
   uint32_t line_bytes; /* bytes fetched per rank per level: 64 or 128 */
   uint32_t kmer_k;     /* length of the k-mer jump table's keys, 0 = no table */
   uint32_t text_check; /* 1 = text + suffix array resident for the verification shortcut */

@@ -34,7 +34,7 @@ def test_c2_build_products(c2):
     C[1:] = np.cumsum(np.bincount(text, minlength=256)).astype(np.uint32)
     assert (idx.C_array() == C).all()
     info = idx.info()
-    assert info.levels == 1 and info.line_bytes == 128 and info.sigma == 5
+    assert info.levels == 1 and info.layout == 3 and info.line_bytes == 64 and info.sigma == 5   # two-bit symbols: csfm_dna.cuh
 
 
 def test_c2_one_million_counts_vs_oracle(c2):

@@ -23,6 +23,22 @@ def fm():
     return csfm_b200
 
 
+def _expected_lookups(info, text, d, o):
+    """Queries that start from the k-mer table: length >= k; on layout 3 the keys are made of the two-bit codes,
+    so a pattern whose last k bytes contain the symbol that occurs once starts from the C array instead."""
+    kk = int(info.kmer_k)
+    lens = np.diff(o).astype(np.int64)
+    use = lens >= kk
+    hist = np.bincount(np.asarray(text, dtype=np.uint8), minlength=256)
+    if info.layout == 3 and (hist > 0).sum() == 5:
+        single = int(np.flatnonzero(hist == 1)[0])
+        ends = o[1:].astype(np.int64)
+        for q in np.flatnonzero(use):
+            if (d[ends[q] - kk: ends[q]] == single).any():
+                use[q] = False
+    return int(use.sum())
+
+
 def _check_queries(fm, idx, case):
     pats = [bytes.fromhex(q["pat_hex"]) for q in case["queries"]]
     d, o = fm.pack_patterns(pats)
@@ -50,15 +66,18 @@ def _check_queries(fm, idx, case):
 
 
 @pytest.mark.parametrize("case", FM["cases"], ids=[c["name"] for c in FM["cases"]])
-@pytest.mark.parametrize("flags", [0, 1, 4, 5, 32], ids=["nib128", "nib128-rawbytes", "bin64", "bin64-8levels", "nib128-textcheck"])
+@pytest.mark.parametrize("flags", [0, 128, 1, 4, 5, 32], ids=["default", "nib128", "nib128-rawbytes", "bin64", "bin64-8levels", "nib128-textcheck"])
 def test_golden_from_text(fm, case, flags):
     """build_from_text on the GPU (SA -> BWT -> C -> wavelet -> SSA) + queries vs the reference."""
     text = bytes.fromhex(case["text_hex"])
     idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=case["stride"]), flags=flags | fm.BUILD_KEEP_SA)
     info = idx.info()
     assert info.n == case["n"]
-    assert info.layout == (1 if flags & 4 else 2) and info.line_bytes == (64 if flags & 4 else 128)
-    assert info.levels == {0: info.levels, 1: 2, 4: info.levels, 5: 8, 32: info.levels}[flags] and 1 <= info.levels <= 8
+    hist = np.bincount(np.frombuffer(text, np.uint8), minlength=256)
+    dna_ok = len(text) > 0 and ((hist > 0).sum() <= 4 or ((hist > 0).sum() == 5 and (hist == 1).any()))
+    want_layout = 1 if flags & 4 else (3 if flags == 0 and dna_ok else 2)   # layout 3 is the default where the text allows it
+    assert info.layout == want_layout and info.line_bytes == (128 if want_layout == 2 else 64)
+    assert info.levels == {0: info.levels, 128: info.levels, 1: 2, 4: info.levels, 5: 8, 32: info.levels}[flags] and 1 <= info.levels <= 8
     assert idx.C_array().tolist() == case["C"]
     assert idx.ssa().tolist() == case["ssa"]
     assert idx.bwt().tobytes() == bytes.fromhex(case["bwt_hex"])
@@ -127,7 +146,7 @@ def _mixed_patterns(rng, text, alpha, k, maxlen):
     return pats
 
 
-@pytest.mark.parametrize("layout", [0, 4], ids=["nib128", "bin64"])
+@pytest.mark.parametrize("layout", [0, 4, 128], ids=["default", "bin64", "nib128"])
 @pytest.mark.parametrize("sigma,n,stride,term,flags", [
     (2, 50_000, 4, True, 0), (4, 200_000, 32, True, 0), (4, 200_000, 32, True, 1), (5, 100_000, 7, False, 0),
     (15, 90_000, 5, True, 0), (16, 90_000, 5, False, 0), (17, 90_000, 5, True, 0),
@@ -158,8 +177,7 @@ def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
         assert st.search_steps == int(osteps.sum())  # the S of the roofline model is counted exactly
     else:
         # queries of length >= k start from the k-mer jump table: same answers, fewer rank steps
-        lens = np.diff(o).astype(np.int64)
-        assert st.table_lookups == int((lens >= kk).sum())
+        assert st.table_lookups == _expected_lookups(idx.info(), text, d, o)
         assert st.search_steps <= int(osteps.sum())
         plain = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=flags | fm.BUILD_NO_KMER_TABLE)
         assert plain.info().kmer_k == 0
@@ -177,6 +195,79 @@ def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
         assert (pos[ok] == opos[ok]).all()
         if (ostatus == 0).all():
             assert lf_gpu == olf
+
+
+@pytest.mark.parametrize("letters,n,stride,where,single", [
+    (4, 150_000, 32, "end", 0x24), (4, 150_000, 8, "middle", 0x24), (4, 40_000, 5, "start", 0xFF), (4, 40_000, 3, "middle", 0x42),
+    (3, 1_000, 4, "end", 0x00), (4, 191, 2, "end", 0x01), (4, 192, 2, "middle", 0x01), (4, 193, 2, "start", 0x01),
+    (4, 383, 7, "middle", 0x7F), (4, 384, 7, "end", 0x7F), (4, 385, 1, "start", 0x7F), (2, 5_000, 16, None, 0), (4, 97, 32, None, 0),
+    (1, 700, 9, "end", 0x00),
+])
+def test_dna_layout_vs_oracle(fm, letters, n, stride, where, single):
+    """Layout 3 (two-bit symbols, 64-byte lines, two-lane sub-warps): <= 4 frequent symbols plus one symbol that
+    occurs once ANYWHERE in the text and anywhere in byte order (not only a smallest terminator), line-boundary
+    sizes (192 symbols per line), failing LF walks, every build product, counts, intervals, positions."""
+    rng = np.random.default_rng(letters * 7919 + n + stride)
+    alpha = np.array([0x41, 0x43, 0x47, 0x54][:letters], dtype=np.uint8)
+    body = alpha[rng.integers(0, letters, n)].astype(np.uint8)
+    if where is not None:
+        at = {"end": n - 1, "middle": n // 2, "start": 0}[where]
+        body[at] = single
+    text = body
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=fm.BUILD_KEEP_SA)
+    info = idx.info()
+    assert info.layout == 3 and info.line_bytes == 64 and info.levels == 1
+    orc = oracle.OracleIndex(text, stride=stride)
+    assert (idx.sa() == orc.sa).all()
+    assert (idx.bwt() == orc.bwt).all()          # access through the two-bit lines, incl. the row of the single symbol
+    assert (idx.C_array() == orc.C).all()
+    assert (idx.ssa() == orc.ssa).all()
+    both = np.concatenate([alpha, np.array([single], np.uint8)]) if where is not None else alpha
+    pats = _mixed_patterns(rng, text, both, 4000, 30)
+    if where is not None:  # patterns through, ending at and starting at the single symbol
+        at = int(np.flatnonzero(text == single)[0])
+        for a, b in ((at - 3, at + 4), (at - 5, at + 1), (at, at + 6), (at, at + 1), (at - 1, at + 1)):
+            a, b = max(a, 0), min(b, n)
+            pats.append(text[a:b].tobytes())
+        pats.append(bytes([single, single]))
+    d, o = fm.pack_patterns(pats)
+    oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
+    for build_flags in (0, fm.BUILD_NO_KMER_TABLE):
+        ix = idx if build_flags == 0 else fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=build_flags)
+        assert ix.info().layout == 3
+        ix.set_instrumentation(1)
+        counts, sp_ep = ix.count_batch(d, o, want_intervals=True)
+        st = ix.last_call_stats()
+        assert (counts == oc).all()
+        assert (sp_ep == ose).all()
+        if ix.info().kmer_k == 0:
+            assert st.search_steps == int(osteps.sum())
+        else:
+            assert st.table_lookups == _expected_lookups(ix.info(), text, d, o)
+        ix.set_instrumentation(0)
+        assert (ix.count_batch(d, o) == oc).all()   # the uninstrumented kernel
+    for limit in (100000, 5):
+        idx.set_instrumentation(1)
+        offs, pos, status = idx.locate_batch(d, o, limit=limit)
+        lf_gpu = idx.last_call_stats().lf_steps
+        ooffs, opos, ostatus, olf = orc.locate_batch(d, o, limit=limit)
+        assert (offs == ooffs).all()
+        assert (status == ostatus).all()
+        ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
+        assert (pos[ok] == opos[ok]).all()
+        if (ostatus == 0).all():
+            assert lf_gpu == olf
+    # the same answers from layout 2 on the same text, from a blob round trip, and one query at a time
+    idx2 = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=fm.BUILD_LAYOUT_NIBBLE128)
+    assert idx2.info().layout == 2
+    assert (idx2.count_batch(d, o) == oc).all()
+    back = fm.FMIndex.from_host_blob(idx.blob_to_host())
+    assert back.info().layout == 3
+    c3, se3 = back.count_batch(d, o, want_intervals=True)
+    assert (c3 == oc).all() and (se3 == ose).all()
+    assert (back.bwt() == orc.bwt).all()
+    for q in range(0, len(pats), max(1, len(pats) // 40)):
+        assert idx.count(pats[q]) == int(oc[q])
 
 
 def test_long_and_many_patterns(fm):
