@@ -184,6 +184,10 @@ void csfm_destroy(csfm_index* idx) {
     sl.out.release();
     sl.scan.release();
   }
+  for (auto& qs : idx->qslot) {
+    qs.buf.release();
+    if (qs.done) cudaEventDestroy(qs.done);
+  }
   if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
   if (idx->d_sa) cudaFree(idx->d_sa);
   idx->ws_in.release();

@@ -79,6 +79,17 @@ struct csfm_index {
     uint64_t sp = 0, count = 0;
   } single_cache;
 
+  // two-pass count (count2q_kernel + the sub-warp kernel over what it left): a small ring of overflow lists, each
+  // guarded by an event so that a list is not reused while an earlier launch may still read it
+  struct QListSlot {
+    csfm::DeviceBuffer buf;
+    cudaEvent_t done = nullptr;
+    uint64_t npat = 0;  // batch size of the launch that used the slot last (0 = never used)
+  } qslot[8];
+  uint32_t qslot_next = 0;
+  uint32_t two_pass_skip = 0;   // calls for which the two-pass form is skipped (most queries of recent batches overflowed)
+  bool no_two_pass = true;      // the two-pass form is opt-in (CSFM_TWO_PASS=1): measured slower than the one-pass sub-warp kernel
+
   uint32_t instr_mask = 0;
   bool tma_staging = false;  // count kernel variant (csfm_set_option / CSFM_PATTERN_STAGING=tma)
   bool no_sa_locate = false;  // CSFM_NO_SA_LOCATE: walk even when the index carries its suffix array

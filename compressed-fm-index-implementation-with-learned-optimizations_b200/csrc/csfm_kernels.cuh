@@ -271,6 +271,11 @@ struct CountArgs {
   uint32_t limit32;
   unsigned long long* cursor;
   unsigned long long* steps_total;  // nullable (instrumentation)
+  // Two-pass count (count2q_kernel, then the sub-warp kernel over what it could not finish): the first pass
+  // appends the queries it leaves to qlist and counts them in *qlist_len; the second pass takes its items
+  // from that list instead of [0, npat). Both null for a one-pass launch.
+  uint32_t* qlist;
+  unsigned long long* qlist_len;
 };
 
 // Single-query path (cs::FMIndex::count / locate called one pattern at a time, tools/benchmark.cpp): the
@@ -302,6 +307,10 @@ struct WalkArgs {
 
 // Layout-2 kernels (csfm_query2.cu); launched by the dispatchers in csfm_query.cu.
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging);
+// One query per THREAD for the queries that finish in "table lookup, (half step,) text verification"; the rest go to a.qlist.
+bool count2q_eligible(const IndexView& iv, const CountArgs& a);
+void launch_count2q(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream);
+int max_blocks_per_sm_count2q(const CountArgs& a);
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream);
 void launch_count_single2(const IndexView& iv, const SingleQuery& q, SingleResult* d_result, cudaStream_t stream);
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);

@@ -349,16 +349,55 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   const uint64_t want = (npat * (dna ? 2 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
-  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
-  if (dna)
-    launch_count3(idx->view, a, grid, stream);
-  else if (nib)
-    launch_count2(idx->view, a, grid, stream, tma);
-  else
-    count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
-  if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
-  CSFM_CUDA(cudaGetLastError());
-  idx->stats.kernel_launches += 1;
+  // Two-pass form on an index with text sections: one query per thread for everything that finishes in "lookup,
+  // half step, verification", then the sub-warp kernel over the queries that pass left in the overflow list.
+  bool two_pass = nib && !tma && !idx->no_two_pass && count2q_eligible(idx->view, a);
+  if (two_pass && idx->two_pass_skip > 0) {
+    --idx->two_pass_skip;
+    two_pass = false;
+  }
+  if (two_pass) {
+    csfm_index::QListSlot& qs = idx->qslot[idx->qslot_next++ % 8];
+    unsigned long long* h_over = static_cast<unsigned long long*>(idx->h_pinned) + 32 + (&qs - idx->qslot);  // bytes 256..319
+    if (!qs.done) CSFM_CUDA(cudaEventCreateWithFlags(&qs.done, cudaEventDisableTiming));
+    if (qs.npat) {
+      if (cudaEventQuery(qs.done) == cudaSuccess) {
+        // how the launch that used this slot last went: mostly overflow => this workload is not the common case
+        // the first pass is made for; skip it for a while and probe again later
+        if (*h_over * 4 > qs.npat) idx->two_pass_skip = 64;
+      } else {
+        (void)cudaGetLastError();
+      }
+      CSFM_CUDA(cudaStreamWaitEvent(stream, qs.done, 0));
+    }
+    int rc = qs.buf.ensure(npat * 4 + 256);
+    if (rc) return rc;
+    qs.npat = npat;
+    a.qlist = qs.buf.as<uint32_t>();
+    a.qlist_len = ctr + 6;
+    if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
+    const int grid1 = (int)std::min<uint64_t>((npat + kThreads - 1) / kThreads, (uint64_t)idx->num_sms * max_blocks_per_sm_count2q(a));
+    launch_count2q(idx->view, a, grid1, stream);
+    CountArgs b = a;
+    b.cursor = ctr + 7;
+    launch_count2(idx->view, b, idx->num_sms * max_blocks_per_sm_count2(false, idx->view, b), stream, false);
+    if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
+    CSFM_CUDA(cudaGetLastError());
+    CSFM_CUDA(cudaMemcpyAsync(h_over, ctr + 6, 8, cudaMemcpyDeviceToHost, stream));
+    CSFM_CUDA(cudaEventRecord(qs.done, stream));
+    idx->stats.kernel_launches += 2;
+  } else {
+    if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
+    if (dna)
+      launch_count3(idx->view, a, grid, stream);
+    else if (nib)
+      launch_count2(idx->view, a, grid, stream, tma);
+    else
+      count_kernel<<<grid, kThreads, 0, stream>>>(idx->view, a);
+    if (timed) CSFM_CUDA(cudaEventRecord(idx->ev1, stream));
+    CSFM_CUDA(cudaGetLastError());
+    idx->stats.kernel_launches += 1;
+  }
   if (a.steps_total) {  // ctr[1] = rank steps, ctr[2] = k-mer table lookups
     CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 8, ctr + 1, 8, cudaMemcpyDeviceToHost, stream));
     CSFM_CUDA(cudaMemcpyAsync((unsigned long long*)idx->h_pinned + 10, ctr + 2, 32, cudaMemcpyDeviceToHost, stream));  // + ctr[4] = half steps, ctr[5] = level lines fetched

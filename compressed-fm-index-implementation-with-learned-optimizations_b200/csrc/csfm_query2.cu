@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, kShortcut ? CSFM_SHORTCUT_CTAS : 8)
 count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ Tables tb;
   __shared__ uint4 step_tab[256];
+  if (a.qlist && *a.qlist_len == 0) return;  // second pass with nothing left (uniform for the whole grid)
   load_step_table(step_tab, iv.hdr);
   load_tables(tb, iv.hdr);
 
@@ -85,6 +86,8 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   const uint8_t* const lv_last = iv.levels_last + j * 32;
   const uint32_t kk = iv.kmer_k;  // 0 = no jump table
   WarpQueue32 wq;
+  // second pass of a two-pass count: the items are the queries the first pass left in a.qlist
+  const uint32_t nitems = a.qlist ? (uint32_t)*a.qlist_len : (uint32_t)a.npat;
 
   // Text-verification shortcut (see csfm_common.cuh): only when no interval is asked for (a
   // verified query yields its count, 0 or 1, but not its final SA row) and the batch bytes are
@@ -145,11 +148,11 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // (the stepping-only variant keeps per-sub-warp refills: batching them was measured to gain
     // nothing there -- equal-length batches fall into step by themselves -- and its bookkeeping
     // cost 12 % on the issue-bound C2 workload)
-    const uint32_t item = queue_take32(wq, !active, lane, a.cursor, (uint32_t)a.npat,
+    const uint32_t item = queue_take32(wq, !active, lane, a.cursor, nitems,
                                        kShortcut && since_refill < iv.refill_wait ? iv.refill_min : 1u, served);
     if (kShortcut) since_refill = served ? 0u : since_refill + 1u;
     if (item != ~0u) {
-      q = item;
+      q = a.qlist ? a.qlist[item] : item;
       const uint64_t o0 = a.offs[q], o1 = a.offs[(uint64_t)q + 1];
       const uint64_t m = o1 - o0;
       active = true;
@@ -267,19 +270,24 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         const bool bad = vstage == 1 && (((uint32_t)j < rows && vp < rem) ||
                                          reinterpret_cast<const uint8_t*>(pal) + 16 * np16 > batch_end);
         const unsigned bads = __ballot_sync(0xFFFFFFFFu, bad);
+        const bool stage_ok = vstage == 1 && !((bads >> (lane & ~3)) & 0xFu);
+        // text windows: the up to three 16-byte chunks of a row's window go out in ONE instruction, lane c copying
+        // chunk c of row r: one memory request per row (rows beyond the first are rare) instead of one per chunk
+#pragma unroll
+        for (uint32_t r = 0; r < kVerifyRows; ++r) {
+          const uint32_t vr = __shfl_sync(0xFFFFFFFFu, vp, (lane & ~3) | (int)r);  // row r's suffix position lives in lane r
+          if (r == 0 || __any_sync(0xFFFFFFFFu, stage_ok && r < rows)) {
+            const uint32_t tal = (vr - rem) & ~15u;
+            const uint32_t nt16 = (vr - tal + 15) >> 4;
+            if (stage_ok && r < rows && (uint32_t)j < nt16) cp_async16(&vs.t[r][16 * j], iv.text + tal + 16 * j);
+          }
+        }
         if (vstage == 1) {
           if ((bads >> (lane & ~3)) & 0xFu) {
             vstage = 0;
             --ptr;
             begin_step(next_byte);
           } else {
-            if ((uint32_t)j < rows) {
-              const uint32_t tal = (vp - rem) & ~15u;
-              const uint32_t nt16 = (vp - tal + 15) >> 4;
-#pragma unroll
-              for (uint32_t c = 0; c < 3; ++c)
-                if (c < nt16) cp_async16(&vs.t[j][16 * c], iv.text + tal + 16 * c);
-            }
             if ((uint32_t)j < np16) cp_async16(&vs.p[16 * j], reinterpret_cast<const uint8_t*>(pal) + 16 * j);
             cp_async_commit();
             vstage = 2;
@@ -338,6 +346,227 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
     if (lane == 0 && u) atomicAdd(a.steps_total + 2, (unsigned long long)u);
     if (lane == 0 && v) atomicAdd(a.steps_total + 3, (unsigned long long)v);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// count, first pass of the two-pass form: ONE QUERY PER THREAD.
+//
+// On an index that carries the text sections almost every query of a realistic batch is "k-mer table lookup,
+// one half step (level-1 line), at most four suffix-array entries, text comparison": four dependent fetches
+// and nothing else. The sub-warp kernel above spends four lanes and ~90 warp instructions per query on that
+// chain and keeps 8 queries per warp in flight (ncu: 7.9 sectors per request, issue slots 57 % busy, 61 % of
+// the stall samples waiting on the chain). Here every lane carries its own query through the same stages in
+// lock-step with its 31 neighbours: every load instruction fetches 32 different lines (32 sectors per request),
+// a warp has 32 chains in flight, and the whole query costs ~10 warp instructions. A query that does not fit
+// the pattern (short, long remainder, wide interval, an interval that straddles two lines, a window that
+// would wrap around the text) is appended to a.qlist and finished by the sub-warp kernel in a second launch.
+// Same arithmetic as count2_kernel<true,.>: fm_index.cpp:79-101 with the text-verification identity of
+// csfm_common.cuh.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldg_u32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+
+// t[0..rem) == p[0..rem), four characters at a time from aligned words (rem <= kVerifyMax). The words that hold
+// the last characters may extend up to three bytes past them: the caller guarantees those bytes are readable.
+__device__ __forceinline__ bool bytes_equal_global(const uint8_t* __restrict__ t, const uint8_t* __restrict__ p, uint32_t rem) {
+  const uint32_t* tw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(t) & ~(uintptr_t)3);
+  const uint32_t* pw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+  const uint32_t ts = (uint32_t)(reinterpret_cast<uintptr_t>(t) & 3) * 8u, ps = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8u;
+  // words needed: those covering [addr, addr + rem)
+  const uint32_t tn = (uint32_t)((reinterpret_cast<uintptr_t>(t) & 3) + rem + 3) >> 2;
+  const uint32_t pn = (uint32_t)((reinterpret_cast<uintptr_t>(p) & 3) + rem + 3) >> 2;
+  uint32_t acc = 0, tlo = __ldg(tw), plo = __ldg(pw);
+#pragma unroll 2
+  for (uint32_t w = 0; 4u * w < rem; ++w) {
+    const uint32_t thi = (w + 1 < tn) ? __ldg(tw + w + 1) : 0u;
+    const uint32_t phi = (w + 1 < pn) ? __ldg(pw + w + 1) : 0u;
+    const uint32_t x = __funnelshift_r(tlo, thi, ts) ^ __funnelshift_r(plo, phi, ps);
+    const uint32_t left = rem - 4u * w;
+    const uint32_t valid = left < 4u ? left : 4u;
+    acc |= x & __funnelshift_rc(0xFFFFFFFFu, 0u, 32u - 8u * valid);
+    tlo = thi;
+    plo = phi;
+  }
+  return acc == 0;
+}
+
+#ifndef CSFM_COUNT2Q_CTAS
+#define CSFM_COUNT2Q_CTAS 4
+#endif
+// rows verified by the per-thread pass (more go to the second pass) and the lane's private staging slot
+constexpr uint32_t kQRows = 2;
+struct alignas(16) QSlot {
+  uint8_t t[kQRows][48];
+  uint8_t p[48];
+  uint8_t pad[16];
+};
+template <bool kInstr>
+__global__ void __launch_bounds__(kThreads, CSFM_COUNT2Q_CTAS)
+count2q_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
+  __shared__ uint4 step_tab[256];
+  __shared__ QSlot qslots[kThreads];
+  load_step_table(step_tab, iv.hdr);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t kk = iv.kmer_k;
+  const bool half = iv.kmer_hi != nullptr;
+  const uint32_t npat = (uint32_t)a.npat;
+  const uint8_t* const batch_end = a.bytes + a.offs[a.npat];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  uint32_t my_lookups = 0, my_halves = 0, my_checks = 0, my_lines = 0;
+
+  // warp-uniform trip count: every lane of a warp runs the same number of rounds (the votes below need all 32)
+  for (uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; q0 < npat; q0 += stride) {
+    const uint32_t q = q0 + lane;
+    const bool live = q < npat;
+    bool leave = false;  // this query goes to the second pass
+    bool done = false;
+    uint32_t cnt = 0;
+    uint64_t o0 = 0, o1 = 0;
+    if (live) {
+      o0 = a.offs[q];
+      o1 = a.offs[(uint64_t)q + 1];
+    }
+    const uint64_t m = o1 - o0;
+    const uint32_t used = kk + (half ? 1u : 0u);  // characters consumed before the verification
+    if (live && (m < used || m > used + kVerifyMax || kk == 0)) leave = true;
+    const bool go = live && !leave;
+
+    // ---- stage 1: key of the last k characters (+ the character in front of them for the half step)
+    uint32_t e = 0, mul = 1;
+    bool present = true;
+    uint4 st = make_uint4(0, 0, 0, 0);
+    if (go) {
+      for (uint32_t i = 0; i < kk; ++i) {
+        const uint4 t = step_tab[a.bytes[o1 - 1 - i]];
+        present = present && !(t.y & 0x80000000u);
+        e += (t.y & 0xFFu) * mul;
+        mul *= iv.kmer_radix;
+      }
+      if (half) {
+        st = step_tab[a.bytes[o1 - 1 - kk]];
+        present = present && !(st.y & 0x80000000u);
+      }
+      if (kInstr) ++my_lookups;
+      if (!present) done = true;  // a character that does not occur: count 0 (fm_index.cpp:96)
+    }
+    // ---- stage 2: table lookup (one 8-byte entry per lane: 32 lines per load instruction)
+    uint32_t sp = 0, ep = 0;
+    if (go && !done) {
+      if (half) {
+        const uint2 se = iv.kmer_hi[(size_t)e * 16u + ((st.y & 0xFFu) >> 4)];
+        sp = se.x;
+        ep = se.y;
+      } else if (iv.kmer_tiled) {
+        const uint32_t* const t32 = reinterpret_cast<const uint32_t*>(iv.kmer);
+        sp = t32[e];
+        ep = t32[(size_t)e + 1];
+      } else {
+        const uint2 se = iv.kmer[e];
+        sp = se.x;
+        ep = se.y;
+      }
+      if (sp >= ep) done = true;
+    }
+    // ---- stage 3 (half-step table): the level-1 half of the pending step, both ends from ONE line.
+    // A lane loads only the 32-byte chunks it needs: those with symbols before `oe`, and the one that holds
+    // the counter of v (every load instruction costs the L1 one tag cycle per distinct line it touches).
+    if (half && go && !done) {
+      if (((sp ^ ep) >> 7) != 0u) {
+        leave = true;  // the interval straddles two lines
+      } else {
+        if (kInstr) { ++my_halves; ++my_lines; }
+        const uint32_t v = st.y & 15u, vc = v >> 2;
+        const uint8_t* const line = iv.levels_last + (sp & ~(kSymsPerLine - 1));  // 128 symbols per 128-byte line
+        const uint32_t os = sp & (kSymsPerLine - 1), oe = ep & (kSymsPerLine - 1);
+        const uint32_t last = oe >> 5;
+        Chunk32 k0 = ldg_nc_v8(line), k1 = chunk_undefined(), k2 = chunk_undefined(), k3 = chunk_undefined();
+        if (last >= 1u || vc == 1u) k1 = ldg_nc_v8(line + 32);
+        if (last >= 2u || vc == 2u) k2 = ldg_nc_v8(line + 64);
+        if (last >= 3u || vc == 3u) k3 = ldg_nc_v8(line + 96);
+        const uint32_t c0 = pick4(k0.c0, k0.c1, k0.c2, k0.c3, v), c1 = pick4(k1.c0, k1.c1, k1.c2, k1.c3, v);
+        const uint32_t c2 = pick4(k2.c0, k2.c1, k2.c2, k2.c3, v), c3 = pick4(k3.c0, k3.c1, k3.c2, k3.c3, v);
+        uint32_t rs = vc == 0u ? c0 : vc == 1u ? c1 : vc == 2u ? c2 : c3, re = rs;
+        uint32_t hw = chunk_hits(k0, v);
+        rs += (uint32_t)__popc(hw & low_mask((int)os));
+        re += (uint32_t)__popc(hw & low_mask((int)oe));
+        hw = chunk_hits(k1, v);  // chunks that were not loaded lie at or beyond oe: their mask is empty
+        rs += (uint32_t)__popc(hw & low_mask((int)os - 32));
+        re += (uint32_t)__popc(hw & low_mask((int)oe - 32));
+        hw = chunk_hits(k2, v);
+        rs += (uint32_t)__popc(hw & low_mask((int)os - 64));
+        re += (uint32_t)__popc(hw & low_mask((int)oe - 64));
+        hw = chunk_hits(k3, v);
+        rs += (uint32_t)__popc(hw & low_mask((int)os - 96));
+        re += (uint32_t)__popc(hw & low_mask((int)oe - 96));
+        sp = st.x + rs;  // fm_index.cpp:92-93
+        ep = st.x + re;
+        if (sp >= ep) done = true;
+      }
+    }
+    // ---- stage 4: what is left of the pattern against the text in front of every row's suffix. The windows
+    // (one per row, one of the pattern) are staged in the lane's own shared-memory slot with 16-byte cp.async
+    // copies, all in flight together, then compared four characters at a time.
+    const uint32_t rem = go ? (uint32_t)(m - used) : 0u;
+    if (go && !done && !leave) {
+      const uint32_t rows = ep - sp;
+      if (rem == 0) {
+        cnt = rows;
+        done = true;
+      } else if (rows > kQRows || rem < iv.verify_min) {
+        leave = true;
+      } else {
+        const uint8_t* const pat = a.bytes + o0;
+        const uintptr_t pal = reinterpret_cast<uintptr_t>(pat) & ~(uintptr_t)15;
+        const uint32_t np16 = (uint32_t)((reinterpret_cast<uintptr_t>(pat + rem) - pal + 15) >> 4);
+        const uint32_t vp0 = iv.dense[sp], vp1 = rows > 1u ? iv.dense[sp + 1] : 0xFFFFFFFFu;
+        // an aligned pattern window that would leave the batch, or an occurrence that would wrap around the text
+        // start (cyclic BWT): that query keeps stepping in the second pass
+        if (reinterpret_cast<const uint8_t*>(pal) + 16 * np16 > batch_end || vp0 < rem || vp1 < rem) {
+          leave = true;
+        } else {
+          if (kInstr) ++my_checks;
+          QSlot& sl = qslots[threadIdx.x];
+          const uint32_t t0 = (vp0 - rem) & ~15u, t1 = (vp1 - rem) & ~15u;
+          const uint32_t n0 = (vp0 - t0 + 15) >> 4, n1 = rows > 1u ? (vp1 - t1 + 15) >> 4 : 0u;
+#pragma unroll
+          for (uint32_t c = 0; c < 3; ++c) {
+            if (c < n0) cp_async16(&sl.t[0][16 * c], iv.text + t0 + 16 * c);
+            if (c < n1) cp_async16(&sl.t[1][16 * c], iv.text + t1 + 16 * c);
+            if (c < np16) cp_async16(&sl.p[16 * c], reinterpret_cast<const uint8_t*>(pal) + 16 * c);
+          }
+          cp_async_commit();
+          cp_async_wait_all();  // the lane's own copies: nobody else reads its slot
+          const uint32_t poff = (uint32_t)(reinterpret_cast<uintptr_t>(pat) & 15u);
+          if (windows_equal(sl.t[0], sl.p, (vp0 - rem) & 15u, poff, rem)) ++cnt;
+          if (rows > 1u && windows_equal(sl.t[1], sl.p, (vp1 - rem) & 15u, poff, rem)) ++cnt;
+          done = true;
+        }
+      }
+    }
+    if (live && done && !leave && a.counts) a.counts[q] = cnt;
+    // ---- queries for the second pass: one atomic per warp
+    const unsigned lv_mask = __ballot_sync(0xFFFFFFFFu, live && leave);
+    if (lv_mask) {
+      unsigned long long slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(a.qlist_len, (unsigned long long)__popc(lv_mask));
+      slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+      if (live && leave) a.qlist[slot0 + __popc(lv_mask & ((1u << lane) - 1u))] = q;
+    }
+  }
+  if (kInstr && a.steps_total) {
+    unsigned t = my_lookups, u = my_checks, v = my_halves, w = my_lines;
+    for (int o = 16; o > 0; o >>= 1) {
+      t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+      u += __shfl_xor_sync(0xFFFFFFFFu, u, o);
+      v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      w += __shfl_xor_sync(0xFFFFFFFFu, w, o);
+    }
+    if (lane == 0 && t) atomicAdd(a.steps_total + 1, (unsigned long long)t);
+    if (lane == 0 && u) atomicAdd(a.steps_total + 2, (unsigned long long)u);
+    if (lane == 0 && v) atomicAdd(a.steps_total + 3, (unsigned long long)v);
+    if (lane == 0 && w) atomicAdd(a.steps_total + 4, (unsigned long long)w);
   }
 }
 
@@ -902,6 +1131,20 @@ int blocks_per_sm(const void* kernel) {
 static bool use_shortcut(const IndexView& iv, const CountArgs& a) {
   return iv.text != nullptr && a.sp_ep == nullptr && a.row_sp == nullptr &&
          (reinterpret_cast<uintptr_t>(a.bytes) & 15) == 0;
+}
+
+// First pass of the two-pass count: needs the text sections with the full suffix array, a k-mer table, no interval
+// outputs. (Unlike the sub-warp verification it does not need the batch bytes to be 16-byte aligned.)
+bool count2q_eligible(const IndexView& iv, const CountArgs& a) {
+  return iv.text != nullptr && iv.dense != nullptr && iv.dense_shift == 0 && iv.kmer_k != 0 && iv.kmer != nullptr &&
+         a.sp_ep == nullptr && a.row_sp == nullptr && a.counts != nullptr;
+}
+void launch_count2q(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream) {
+  if (a.steps_total) count2q_kernel<true><<<grid, kThreads, 0, stream>>>(iv, a);
+  else count2q_kernel<false><<<grid, kThreads, 0, stream>>>(iv, a);
+}
+int max_blocks_per_sm_count2q(const CountArgs& a) {
+  return a.steps_total ? blocks_per_sm((const void*)count2q_kernel<true>) : blocks_per_sm((const void*)count2q_kernel<false>);
 }
 
 void launch_count2(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, bool tma_staging) {

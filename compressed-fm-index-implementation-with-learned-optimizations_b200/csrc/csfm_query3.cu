@@ -139,7 +139,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           }
         }
         if (!present) {
-          if (kInstr) ++my_lookups;  // answered without a step: one of the k characters does not occur
+          if (kInstr && keyed) ++my_lookups;  // answered without a step: one of the k characters does not occur
           finish(0, 0, 0);
         } else if (keyed) {
           if (kInstr) ++my_lookups;

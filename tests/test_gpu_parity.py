@@ -405,9 +405,10 @@ def test_tma_staged_count_variant(fm, monkeypatch):
     buffer per warp) must agree with the oracle exactly like the default direct-load kernel."""
     monkeypatch.setenv("CSFM_PATTERN_STAGING", "tma")
     rng = np.random.default_rng(77)
-    for sigma, n, flags in [(4, 150_000, 0), (200, 200_000, 0)]:
+    for sigma, n, flags in [(4, 150_000, fm.BUILD_LAYOUT_NIBBLE128), (200, 200_000, 0)]:  # the staged variant is a layout-2 kernel
         text, alpha = _rand_text(rng, n, sigma, True)
         idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16), flags=flags)
+        assert idx.info().layout == 2
         orc = oracle.OracleIndex(text, stride=16)
         pats = _mixed_patterns(rng, text, alpha, 20_000, 40)
         pats += [text[s:s + m].tobytes() for s, m in zip(rng.integers(0, n - 3000, 40), rng.integers(65, 2500, 40))]
@@ -672,7 +673,34 @@ def test_text_verification_shortcut(fm, sigma, n):
     st = idx.last_call_stats()
     assert (got == oc).all()
     assert st.text_checks > 1000                       # the shortcut really ran
+    assert st.kernel_launches == 1
+    idx.set_instrumentation(0)
+    assert (idx.count_batch(d, o) == oc).all()         # the uninstrumented kernel
     assert (plain.count_batch(d, o) == oc).all()
+    # the two-pass form (one query per thread, then the sub-warp kernel over what it left; opt-in, measured
+    # slower on B200: profiles/README.md) must agree
+    os.environ["CSFM_TWO_PASS"] = "1"
+    try:
+        two = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=32), flags=fm.BUILD_FORCE_TEXT_CHECK)
+    finally:
+        del os.environ["CSFM_TWO_PASS"]
+    two.set_instrumentation(1)
+    assert (two.count_batch(d, o) == oc).all()
+    assert two.last_call_stats().kernel_launches == 2 and two.last_call_stats().text_checks > 1000
+    two.set_instrumentation(0)
+    assert (two.count_batch(d, o) == oc).all()
+    # a device batch that is not 4-byte aligned, and a pattern that ends on the last byte of the batch
+    import torch
+    dev = torch.device("cuda", 0)
+    for shift in (1, 2, 3, 5):
+        tb = torch.zeros(d.size + 8, dtype=torch.uint8, device=dev)
+        tb[shift: shift + d.size] = torch.from_numpy(d).to(dev)
+        to = torch.from_numpy(o.astype(np.int64)).to(dev)
+        for ix in (idx, two):
+            tc = torch.zeros(len(pats), dtype=torch.int64, device=dev)
+            ix.count_batch_device(tb.data_ptr() + shift, to.data_ptr(), len(pats), tc.data_ptr(), 0, 0)
+            torch.cuda.synchronize()
+            assert (tc.cpu().numpy().astype(np.uint64) == oc).all(), shift
     # with intervals requested the shortcut is off and the intervals are exact
     c2, se2 = idx.count_batch(d, o, want_intervals=True)
     oc2, ose2 = orc.count_batch(d, o)
