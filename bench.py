@@ -614,10 +614,11 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
     if rank == 0:
         construction = {"n": n, "seconds": build_s, "suffixes_per_s": n / build_s, "sa_rounds": int(info.sa_rounds),
                         "sa_radix_passes": int(info.sa_radix_passes),
-                        "sort_bytes_moved_model": n * int(info.sa_radix_passes) * 2 * 12,
+                        "sa_pair_passes": int(info.sa_pair_passes),
+                        "sort_bytes_moved_model": int(info.sa_pair_passes) * 2 * 12,
                         "note": "csfm_build_from_text_device on device-resident text: suffix array (packed-key radix sort + prefix "
-                                "doubling), BWT, SSA, levels, k-mer and half-step tables, text sections; the model figure is n x "
-                                "8-bit radix passes x 2 x (8 B key + 4 B suffix)"}
+                                "doubling over the unresolved suffixes), BWT, SSA, levels, k-mer and half-step tables, text sections; the model "
+                                "figure is pairs sorted x 8-bit radix passes (summed over rounds) x 2 x (8 B key + 4 B suffix)"}
     log(f"[rank {rank}] n={n} levels={L} sigma={info.sigma} blob={info.blob_bytes/1e6:.1f} MB text_gen={t_text:.2f}s "
         f"build={build_s if build_s is None else round(build_s, 2)}s bcast_ms={bcast_ms}")
 

@@ -50,7 +50,7 @@ class IndexInfo(C.Structure):
                 ("device", C.c_uint32), ("nsamp", C.c_uint64), ("blocks_per_level", C.c_uint64),
                 ("blob_bytes", C.c_uint64), ("has_sa", C.c_uint32), ("layout", C.c_uint32), ("line_bytes", C.c_uint32),
                 ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("half_table", C.c_uint32),
-                ("sa_rounds", C.c_uint32), ("sa_radix_passes", C.c_uint32)]
+                ("sa_rounds", C.c_uint32), ("sa_radix_passes", C.c_uint32), ("sa_pair_passes", C.c_uint64)]
 
 
 class CallStats(C.Structure):
@@ -76,6 +76,7 @@ SIGNATURES = {
     "csfm_sa_device": (C.c_int, [_vp, C.POINTER(_vp)]),
     "csfm_release_sa": (C.c_int, [_vp]),
     "csfm_extract_bwt": (C.c_int, [_vp, _vp]),
+    "csfm_extract": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_blob": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "csfm_attach_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(_vp)]),
     "csfm_replicate": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
@@ -367,8 +368,11 @@ class FMIndex:
 
     def extract(self, pos: int, length: int) -> bytes:
         """cs::FMIndex::extract (fm_index.cpp:163-167): host substring, clamped."""
-        if self._text is None:
-            raise RuntimeError("extract: the index was not built from text on this host")
+        if self._text is None:  # no host copy (attached / loaded blob): from the index itself
+            out = np.zeros(max(1, int(length)), np.uint8)
+            got = C.c_uint64()
+            _check(lib().csfm_extract(self._h, int(pos), int(length), _np_ptr(out), C.byref(got)))
+            return out[: got.value].tobytes()
         if pos >= len(self._text):
             return b""
         return self._text[pos: pos + min(length, len(self._text) - pos)]

@@ -64,6 +64,15 @@ static int check_device(int device) {
 
 static uint32_t stride_of(const csfm_params* p) { return p ? p->ssa_stride : 32u; }
 
+// Host-pointer entry points check what the kernels trust: offsets must not decrease (a decreasing pair would
+// give a pattern length near 2^64 and a walk far outside the staged bytes). One pass over npat + 1 words.
+template <class T>
+static bool offsets_monotone(const T* offs, uint64_t npat) {
+  T bad = 0;
+  for (uint64_t i = 0; i < npat; ++i) bad |= (T)(offs[i + 1] < offs[i]);
+  return bad == 0;
+}
+
 }  // namespace csfm
 
 using namespace csfm;
@@ -99,7 +108,9 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
   uint64_t nsamp = 0;
   const bool want_sa = (flags & CSFM_BUILD_KEEP_SA) || !((flags & CSFM_BUILD_NO_TEXT_CHECK) || (flags & CSFM_BUILD_LAYOUT_BINARY64));
   uint32_t sa_rounds = 0, sa_passes = 0;
-  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp, want_sa ? &d_sa : nullptr, &sa_rounds, &sa_passes);
+  uint64_t sa_pair_passes = 0;
+  rc = build_sa_bwt_device(d_text, n, stride, nullptr, &d_bwt, &d_ssa, &nsamp, want_sa ? &d_sa : nullptr, &sa_rounds, &sa_passes,
+                           &sa_pair_passes);
   if (rc) return rc;
   rc = index_from_device_bwt(d_bwt, n, d_ssa, nsamp, stride, device, flags, out, d_text, d_sa);
   cudaFree(d_bwt);
@@ -110,6 +121,7 @@ int csfm_build_from_text_device(const uint8_t* d_text, uint64_t n, const csfm_pa
   }
   (*out)->sa_rounds = sa_rounds;
   (*out)->sa_radix_passes = sa_passes;
+  (*out)->sa_pair_passes = sa_pair_passes;
   if (flags & CSFM_BUILD_KEEP_SA)
     (*out)->d_sa = d_sa;
   else
@@ -190,6 +202,7 @@ void csfm_destroy(csfm_index* idx) {
   }
   if (idx->owns_blob && idx->d_blob) cudaFree(idx->d_blob);
   if (idx->d_sa) cudaFree(idx->d_sa);
+  if (idx->d_text_cache) cudaFree(idx->d_text_cache);
   idx->ws_in.release();
   idx->ws_out.release();
   idx->ws_tmp.release();
@@ -227,6 +240,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->half_table = idx->view.kmer_hi != nullptr;
   out->sa_rounds = idx->sa_rounds;
   out->sa_radix_passes = idx->sa_radix_passes;
+  out->sa_pair_passes = idx->sa_pair_passes;
   return CSFM_OK;
 }
 
@@ -279,6 +293,57 @@ int csfm_extract_bwt(const csfm_index* cidx, uint8_t* out) {
   if (rc) return rc;
   CSFM_CUDA(cudaMemcpyAsync(out, idx->ws_out.p, idx->h.n, cudaMemcpyDeviceToHost, idx->stream));
   CSFM_CUDA(cudaStreamSynchronize(idx->stream));
+  return CSFM_OK;
+}
+
+// cs::FMIndex::extract (fm_index.cpp:163-167) without a host copy of the text: from the blob's text section when
+// it has one, else from a device copy of the text that is rebuilt ONCE out of the index itself (every sampled row
+// walks LF to the next sampled row and writes the BWT symbols it passes: n LF steps in all).
+int csfm_extract(csfm_index* idx, uint64_t pos, uint64_t len, uint8_t* out, uint64_t* got) {
+  if (!idx || !got || (len && !out)) return fail(CSFM_ERR_INVALID, "null argument");
+  *got = 0;
+  const uint64_t n = idx->h.n;
+  if (pos >= n || len == 0) return CSFM_OK;  // fm_index.cpp:164
+  len = std::min(len, n - pos);
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lk(idx->mu);
+  const uint8_t* src = idx->h.off_text ? idx->d_blob + idx->h.off_text : idx->d_text_cache;
+  if (!src) {
+    if (idx->h.layout == kLayoutBinary64) return fail(CSFM_ERR_INVALID, "extract from the index needs layout 2 or 3 (or a text section)");
+    // LF(row of suffix p) is the row of suffix p - 1 only when the text ends in a unique smallest byte (else the
+    // reference's BWT is not a rotation BWT: its locate() over-counts or throws there too): the smallest byte present
+    // occurs once, and row 0 — always sampled — is the suffix that starts at n - 1
+    {
+      int c = 0;
+      while (c < 256 && idx->h.C[c + 1] == idx->h.C[c]) ++c;
+      uint32_t sa0 = 0;
+      CSFM_CUDA(cudaMemcpy(&sa0, idx->d_blob + idx->h.off_ssa, 4, cudaMemcpyDeviceToHost));
+      if (c == 256 || idx->h.C[c + 1] - idx->h.C[c] != 1 || (uint64_t)sa0 != n - 1)
+        return fail(CSFM_ERR_INVALID, "extract: the text cannot be rebuilt from this index (it does not end in a unique smallest byte)");
+    }
+    uint8_t* d = nullptr;
+    CSFM_CUDA(cudaMalloc(&d, n));
+    unsigned long long* ctr = next_counter_slot(idx);
+    cudaError_t e = cudaMemsetAsync(ctr, 0, kCounterWords * sizeof(unsigned long long), idx->stream);
+    if (e == cudaSuccess) {
+      if (idx->h.layout == kLayoutDna64) launch_untext3(idx->view, d, ctr, ctr + 1, idx->num_sms, idx->stream);
+      else launch_untext2(idx->view, d, ctr, ctr + 1, idx->num_sms, idx->stream);
+      e = cudaGetLastError();
+    }
+    unsigned long long written = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&written, ctr + 1, 8, cudaMemcpyDeviceToHost, idx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(idx->stream);
+    if (e != cudaSuccess || written != n) {
+      cudaFree(d);
+      if (e != cudaSuccess) return fail(CSFM_ERR_CUDA, std::string("extract: ") + cudaGetErrorString(e));
+      return fail(CSFM_ERR_INVALID, "extract: the text cannot be rebuilt from this index (LF cycles without a sampled row)");
+    }
+    idx->d_text_cache = d;
+    src = d;
+  }
+  CSFM_CUDA(cudaMemcpyAsync(out, src + pos, len, cudaMemcpyDeviceToHost, idx->stream));
+  CSFM_CUDA(cudaStreamSynchronize(idx->stream));
+  *got = len;
   return CSFM_OK;
 }
 
@@ -521,6 +586,7 @@ int csfm_count_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* offs
   if (npat == 0) return CSFM_OK;
   const uint64_t nbytes = offs[npat];
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  if (!offsets_monotone(offs, npat)) return fail(CSFM_ERR_INVALID, "pattern offsets must not decrease");
   DeviceGuard g(idx->device);
   std::lock_guard<std::mutex> lk(idx->mu);
   if (npat == 1 && offs[1] >= offs[0] && single_path_ok(idx, offs[1] - offs[0])) {  // cs::FMIndex::count(pattern)
@@ -674,6 +740,7 @@ int csfm_count_batch_submit(csfm_index* idx, const uint8_t* bytes, const uint64_
   if (!idx || !ticket || (npat && (!offs || !counts))) return fail(CSFM_ERR_INVALID, "null argument");
   const uint64_t nbytes = npat ? offs[npat] : 0;
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  if (npat && !offsets_monotone(offs, npat)) return fail(CSFM_ERR_INVALID, "pattern offsets must not decrease");
   return submit_batch(idx, bytes, nbytes, PatternIndex::kOffsets64, offs, npat, counts, sp_ep, nullptr, ticket);
 }
 
@@ -682,6 +749,7 @@ int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, const uint3
   if (!idx || !ticket || (npat && (!offs32 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
   const uint64_t nbytes = npat ? offs32[npat] : 0;
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  if (npat && !offsets_monotone(offs32, npat)) return fail(CSFM_ERR_INVALID, "pattern offsets must not decrease");
   return submit_batch(idx, bytes, nbytes, PatternIndex::kOffsets32, offs32, npat, nullptr, nullptr, counts32, ticket);
 }
 
@@ -739,6 +807,7 @@ int csfm_locate_batch(csfm_index* idx, const uint8_t* bytes, const uint64_t* off
   }
   const uint64_t nbytes = offs[npat];
   if (nbytes && !bytes) return fail(CSFM_ERR_INVALID, "bytes is null");
+  if (!offsets_monotone(offs, npat)) return fail(CSFM_ERR_INVALID, "pattern offsets must not decrease");
   DeviceGuard g(idx->device);
   std::lock_guard<std::mutex> lk(idx->mu);
   if (npat == 1 && offs[1] >= offs[0] && single_path_ok(idx, offs[1] - offs[0]) && limit <= 0xFFFFFFFFull) {

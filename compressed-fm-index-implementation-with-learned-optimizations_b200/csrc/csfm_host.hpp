@@ -52,6 +52,7 @@ struct csfm_index {
   csfm::IndexView view{};
   uint32_t* d_sa = nullptr;  // CSFM_BUILD_KEEP_SA
   uint32_t sa_rounds = 0, sa_radix_passes = 0;  // how the suffix sort of build_from_text went (0: index not built here)
+  uint64_t sa_pair_passes = 0;
 
   cudaStream_t stream = nullptr;  // used by the host-pointer API
   cudaStream_t aux_stream[2] = {nullptr, nullptr};  // slice pipeline of large host-pointer batches
@@ -90,6 +91,8 @@ struct csfm_index {
   uint32_t two_pass_skip = 0;   // calls for which the two-pass form is skipped (most queries of recent batches overflowed)
   bool no_two_pass = true;      // the two-pass form is opt-in (CSFM_TWO_PASS=1): measured slower than the one-pass sub-warp kernel
 
+  uint8_t* d_text_cache = nullptr;  // csfm_extract on an index without a text section: the text, rebuilt once by LF walks
+
   uint32_t instr_mask = 0;
   bool tma_staging = false;  // count kernel variant (csfm_set_option / CSFM_PATTERN_STAGING=tma)
   bool no_sa_locate = false;  // CSFM_NO_SA_LOCATE: walk even when the index carries its suffix array
@@ -115,7 +118,7 @@ int build_kmer_table3(csfm_index* idx, cudaStream_t stream);  // csfm_query3.cu:
 int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cudaStream_t stream,
                         uint8_t** d_bwt_out, uint32_t** d_ssa_out, uint64_t* nsamp_out,
                         uint32_t** d_sa_out /*nullable: keep SA*/, uint32_t* rounds_out = nullptr,
-                        uint32_t* passes_out = nullptr);
+                        uint32_t* passes_out = nullptr, uint64_t* pair_passes_out = nullptr);
 // csfm_query.cu
 int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t npat,
                  uint64_t* d_counts, uint64_t* d_sp_ep, uint32_t* d_row_sp, uint32_t* d_row_cnt,

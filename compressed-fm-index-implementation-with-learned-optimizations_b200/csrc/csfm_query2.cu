@@ -1090,6 +1090,55 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
 }
 
 // ------------------------------------------------------------------------------------------
+// untext: the text back out of the index (cs::FMIndex::extract on an index that was loaded without its TEXT
+// section, fm_index.cpp:163-167). One sub-warp per SAMPLED row k: it starts at text position ssa[k] and walks LF
+// until the next sampled row, writing BWT[row] = T[position - 1] at every step. LF is a permutation, so the walks
+// of all sampled rows together visit every row exactly once (rows on an LF cycle without a sampled row — texts
+// whose locate() throws — are never reached: the caller compares the number of bytes written with n).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 8)
+untext2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, unsigned long long* __restrict__ cursor,
+               unsigned long long* __restrict__ written) {
+  __shared__ Tables tb;
+  load_tables(tb, iv.hdr);
+  const int lane = threadIdx.x & 31;
+  const int j = lane & 3;
+  const bool two = iv.L == 2;
+  const uint8_t* const lv0 = iv.levels + j * 32;
+  const uint8_t* const lv1 = iv.levels_last + j * 32;
+  WarpQueue wq;
+  bool active = false;
+  uint32_t p = 0, pos = 0, steps = 0, my_written = 0;
+  for (;;) {
+    const unsigned long long item = queue_take(wq, !active, lane, cursor, iv.nsamp);
+    if (item != ~0ull) {
+      p = (uint32_t)item * iv.stride;
+      pos = iv.ssa[item];
+      steps = 0;
+      active = true;
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+    uint32_t v, code = 0;
+    uint32_t r = access_rank_level(lv0, p, active, lane, j, v);
+    if (two) {
+      code = v << 4;
+      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v);
+    }
+    code |= v;
+    if (active) {
+      pos = pos == 0 ? iv.n - 1 : pos - 1;  // BWT[row] = T[(SA[row] - 1) mod n]  (bwt.hpp:10-13)
+      if (j == 0) out[pos] = tb.byte_of_code[code];
+      ++my_written;
+      p = tb.base_by_code[code] + r;
+      if (row_is_sampled(iv, p) || ++steps >= iv.n) active = false;
+    }
+  }
+  unsigned s = (j == 0) ? my_written : 0;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0 && s) atomicAdd(written, (unsigned long long)s);
+}
+
+// ------------------------------------------------------------------------------------------
 // access: BWT[i] for all i (wavelet.cpp:102-128) — verification / export, not a query path
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -1207,6 +1256,12 @@ void launch_count_single2(const IndexView& iv, const SingleQuery& q, SingleResul
 }
 void launch_walk2(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
   walk2_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+}
+void launch_untext2(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms,
+                    cudaStream_t stream) {
+  const unsigned long long want = ((unsigned long long)iv.nsamp * 4 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), (unsigned long long)num_sms * blocks_per_sm((const void*)untext2_kernel));
+  untext2_kernel<<<grid, kThreads, 0, stream>>>(iv, out, cursor, written);
 }
 void launch_access2(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
   access2_kernel<<<grid, kThreads, 0, stream>>>(iv, out);

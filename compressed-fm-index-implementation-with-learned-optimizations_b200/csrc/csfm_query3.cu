@@ -338,6 +338,48 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
   }
 }
 
+// untext (see untext2_kernel in csfm_query2.cu): the text back out of the index, one two-lane sub-warp per sampled row
+__global__ void __launch_bounds__(kThreads, 8)
+untext3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, unsigned long long* __restrict__ cursor,
+               unsigned long long* __restrict__ written) {
+  __shared__ uint32_t base_by_code[8];
+  __shared__ uint8_t byte_of_code[8];
+  if (threadIdx.x < 8) {
+    base_by_code[threadIdx.x] = iv.hdr->base_by_code[threadIdx.x];
+    byte_of_code[threadIdx.x] = iv.hdr->byte_of_code[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int h = lane & 1;
+  const uint8_t* const lv = iv.levels + h * 32;
+  const uint32_t px = iv.special_row;
+  WarpQueue wq;
+  bool active = false;
+  uint32_t p = 0, pos = 0, steps = 0, my_written = 0;
+  for (;;) {
+    const unsigned long long item = queue_takeg<2>(wq, !active, lane, cursor, iv.nsamp);
+    if (item != ~0ull) {
+      p = (uint32_t)item * iv.stride;
+      pos = iv.ssa[item];
+      steps = 0;
+      active = true;
+    }
+    if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
+    uint32_t v;
+    const uint32_t r = access_rank3(lv, p, active, lane, h, v);
+    if (active) {
+      pos = pos == 0 ? iv.n - 1 : pos - 1;  // BWT[row] = T[(SA[row] - 1) mod n]  (bwt.hpp:10-13)
+      if (h == 0) out[pos] = p == px ? (uint8_t)iv.special_byte : byte_of_code[v];
+      ++my_written;
+      p = p == px ? iv.special_first : base_by_code[v] + r - ((v == 0u && p > px) ? 1u : 0u);
+      if (row_is_sampled(iv, p) || ++steps >= iv.n) active = false;
+    }
+  }
+  unsigned s = (h == 0) ? my_written : 0;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0 && s) atomicAdd(written, (unsigned long long)s);
+}
+
 // ------------------------------------------------------------------------------------------
 // access: BWT[i] for all i (wavelet.cpp:102-128) — verification / export, not a query path
 // ------------------------------------------------------------------------------------------
@@ -375,6 +417,12 @@ void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream
 }
 void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
   walk3_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+}
+void launch_untext3(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms,
+                    cudaStream_t stream) {
+  const unsigned long long want = ((unsigned long long)iv.nsamp * 2 + kThreads - 1) / kThreads;
+  const int grid = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), (unsigned long long)num_sms * blocks_per_sm3((const void*)untext3_kernel));
+  untext3_kernel<<<grid, kThreads, 0, stream>>>(iv, out, cursor, written);
 }
 void launch_access3(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
   access3_kernel<<<grid, kThreads, 0, stream>>>(iv, out);

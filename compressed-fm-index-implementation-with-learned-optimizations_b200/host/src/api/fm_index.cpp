@@ -181,13 +181,13 @@ std::vector<uint64_t> FMIndex::locate(std::string_view pattern, size_t limit) co
   return std::move(r.positions);
 }
 
-void FMIndex::save(const std::string& path) const {
+void FMIndex::save(const std::string& path, bool include_text) const {
   if (!handle_) throw std::runtime_error("save: index not built");
   csfm_index_info info;
   if (csfm_info(handle_.get(), &info) != CSFM_OK) throw_last("save");
   CsidxSections s;
   s.text_len = meta_.n;
-  if (text_) {
+  if (text_ && include_text) {
     s.has_text = true;
     s.text = *text_;
   }
@@ -225,6 +225,16 @@ FMIndex FMIndex::load(const std::string& path) {
 }
 
 std::string FMIndex::extract(uint64_t p, uint64_t len) const {
+  if (!text_ && handle_) {
+    // loaded without a TEXT section: the text comes back out of the device index (csfm_extract)
+    if (p >= meta_.n) return {};  // fm_index.cpp:164
+    len = len < meta_.n - p ? len : meta_.n - p;
+    std::string out(len, '\0');
+    uint64_t got = 0;
+    if (csfm_extract(handle_.get(), p, len, reinterpret_cast<uint8_t*>(out.data()), &got) != CSFM_OK) throw_last("extract");
+    out.resize(got);
+    return out;
+  }
   if (!text_ || p >= text_->size()) return {};  // fm_index.cpp:164
   len = len < text_->size() - p ? len : text_->size() - p;
   return text_->substr(p, len);

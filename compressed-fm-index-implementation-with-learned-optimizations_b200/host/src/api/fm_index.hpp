@@ -69,7 +69,9 @@ public:
 
   // ---- persistence (new): the reference's .csidx container (src/serialization/serialization.hpp)
   /// Writes TEXT, BWT, C_ARRAY, SSA and the device-resident index blob (host/src/serialization/csidx.hpp).
-  void save(const std::string& path) const;
+  /// include_text = false leaves the TEXT section out: extract() on the loaded index then reads the text back
+  /// out of the device index (csfm_extract).
+  void save(const std::string& path, bool include_text = true) const;
   /// Loads a file written by save(): one read + one host->device copy, no rebuild. Files without
   /// the device blob are rebuilt from their BWT + SSA sections.
   static FMIndex load(const std::string& path);

@@ -15,7 +15,9 @@
  *    as void*; they only enqueue work (results are ready when the stream reaches that point),
  *    except where a host-visible total is returned (documented per function);
  *  - patterns travel packed: `bytes` holds all pattern bytes back to back, `offs[npat+1]`
- *    (uint64) the start of each pattern, offs[npat] = total bytes. Patterns are borrowed;
+ *    (uint64) the start of each pattern, offs[npat] = total bytes. Patterns are borrowed. Offsets must not
+ *    decrease: the host-pointer entry points check that (CSFM_ERR_INVALID); for the "_device" forms it is a
+ *    PRECONDITION (the offsets live on the device and the kernels trust them);
  *  - all results are bit-exact with the reference on the same text and patterns, including its
  *    quirks: count("") == n, cyclic over-count without a terminator, locate
  *    positions in SA-row order, an error status where the reference throws;
@@ -114,8 +116,10 @@ typedef struct {
                           query needs only its second level) */
   uint32_t sa_rounds;  /* build_from_text: sorting rounds of the suffix sort (1 = the packed first
                           symbols already separated every suffix), 0 if the index was not built here */
-  uint32_t sa_radix_passes; /* 8-bit radix passes over the (u64 key, u32 suffix) pairs, all rounds:
-                               the sort moved about n * passes * 2 * 12 bytes */
+  uint32_t sa_radix_passes; /* 8-bit radix passes of the rounds that sorted ALL n (u64 key, u32 suffix) pairs */
+  uint64_t sa_pair_passes;  /* sum over all rounds of pairs sorted x 8-bit passes: the sort moved about
+                               sa_pair_passes * 2 * 12 bytes. Rounds after the first sort only the suffixes whose
+                               group still has more than one member once those are at most half of the text */
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */
@@ -168,6 +172,14 @@ CSFM_API int csfm_sa_device(const csfm_index* idx, const uint32_t** d_sa);
 CSFM_API int csfm_release_sa(csfm_index* idx);
 /* BWT re-derived from the wavelet matrix by an access kernel (wavelet.cpp:102-128). */
 CSFM_API int csfm_extract_bwt(const csfm_index* idx, uint8_t* out /*n*/);
+
+/* cs::FMIndex::extract (fm_index.cpp:163-167) from the index itself, for handles that have no host copy of the text
+ * (an index loaded from a .csidx without its TEXT section, an attached blob): out receives T[pos, pos + *got),
+ * *got = min(len, n - pos), 0 when pos >= n. Served from the blob's text section when it has one, else from a device
+ * copy of the text rebuilt once out of the index (n LF steps in all, layouts 2 and 3). CSFM_ERR_INVALID when the
+ * text cannot be rebuilt: it must end in a unique smallest byte (otherwise the reference's BWT is not a rotation
+ * BWT and LF does not walk the text backwards; locate() over-counts or throws on such texts too). */
+CSFM_API int csfm_extract(csfm_index* idx, uint64_t pos, uint64_t len, uint8_t* out, uint64_t* got);
 
 /* ---- replication: the whole index is one contiguous device blob --------------------------- */
 /* Pointer/size of the blob on the index's device. Broadcast it (one ncclBroadcast) and attach. */

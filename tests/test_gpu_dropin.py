@@ -103,6 +103,13 @@ int main(int argc, char** argv) {
   auto loc2 = back.locate_batch(views, 17);
   assert(loc2.offsets == loc.offsets && loc2.positions == loc.positions && loc2.status == loc.status);
   assert(back.extract(4, 5) == text.substr(4, 5));
+  // a file without its TEXT section: extract() reads the text back out of the device index (fm_index.cpp:163-167)
+  const std::string path2 = std::string(argv[1]) + "/index_notext.csidx";
+  idx.save(path2, false);
+  cs::FMIndex lean = cs::FMIndex::load(path2);
+  assert(lean.count_batch(pats) == counts);
+  assert(lean.extract(0, text.size() + 10) == text && lean.extract(4, 5) == text.substr(4, 5));
+  assert(lean.extract(text.size() - 3, 100) == text.substr(text.size() - 3) && lean.extract(text.size(), 3).empty());
   // replicas in one process: one per visible GPU (at least two handles, on the same device if there is only one)
   int ndev = 0;
   assert(csfm_device_count(&ndev) == 0 && ndev >= 1);

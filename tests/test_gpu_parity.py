@@ -270,6 +270,42 @@ def test_dna_layout_vs_oracle(fm, letters, n, stride, where, single):
         assert idx.count(pats[q]) == int(oc[q])
 
 
+@pytest.mark.parametrize("sigma,n,stride,flags", [(4, 70_000, 32, 0), (4, 70_000, 5, 128), (60, 90_000, 16, 0), (200, 50_000, 7, 32),
+                                                  (3, 1_000, 1, 0), (255, 300, 4, 0)])
+def test_extract_from_the_index(fm, sigma, n, stride, flags):
+    """cs::FMIndex::extract (fm_index.cpp:163-167) on a handle that has no host copy of the text: csfm_extract serves
+    it from the blob's text section, or rebuilds the text out of the index (every sampled row walks LF to the next)."""
+    rng = np.random.default_rng(sigma + n)
+    text, _ = _rand_text(rng, n, sigma, True)
+    built = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=flags)
+    idx = fm.FMIndex.from_host_blob(built.blob_to_host())    # no host text behind this handle
+    raw = text.tobytes()
+    assert idx.extract(0, len(raw)) == raw
+    for p, l in [(0, 1), (5, 17), (len(raw) - 4, 100), (len(raw) - 1, 1), (len(raw), 5), (len(raw) + 7, 1), (123, 0)]:
+        assert idx.extract(p, l) == raw[p:p + l] if p < len(raw) else idx.extract(p, l) == b""
+    assert built.extract(3, 9) == raw[3:12]                  # the host-text path of the reference
+
+
+def test_extract_needs_a_terminated_text(fm):
+    idx = fm.FMIndex.from_host_blob(fm.FMIndex.build_from_text(b"abab" * 50, fm.BuildParams(ssa_stride=7)).blob_to_host())
+    with pytest.raises(fm.CsfmError, match="cannot be rebuilt"):
+        idx.extract(0, 10)
+    lay1 = fm.FMIndex.from_host_blob(fm.FMIndex.build_from_text(b"banana$", fm.BuildParams(ssa_stride=2),
+                                                                flags=fm.BUILD_LAYOUT_BINARY64).blob_to_host())
+    with pytest.raises(fm.CsfmError, match="layout 2 or 3"):
+        lay1.extract(0, 3)
+
+
+def test_host_offsets_are_checked(fm):
+    idx = fm.FMIndex.build_from_text(b"mississippi$", fm.BuildParams(ssa_stride=4))
+    d = np.frombuffer(b"ssiissi", np.uint8)
+    bad = np.array([0, 5, 3, 7], np.uint64)
+    with pytest.raises(fm.CsfmError, match="must not decrease"):
+        idx.count_batch(d, bad)
+    with pytest.raises(fm.CsfmError, match="must not decrease"):
+        idx.locate_batch(d, bad)
+
+
 def test_long_and_many_patterns(fm):
     rng = np.random.default_rng(99)
     text, alpha = _rand_text(rng, 400_000, 4, True)
