@@ -798,13 +798,36 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
         h_lens8.append(l8)
     h_out8 = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
 
+    # smallest form (csfm_count_batch_submit_packed): for alphabets of at most 16 symbols the patterns travel as the
+    # index's wire codes, `bits` per symbol (3 for DNA + terminator); the client holds them packed (untimed setup)
+    codes_np, wire_bits = idx.pattern_codes()
+    h_packed = []
+    if wire_bits <= 4:
+        lut = torch.from_numpy(codes_np.astype(np.int64)).to(dev)
+        weights = (1 << torch.arange(8, device=dev, dtype=torch.int64))
+        for bytes_d, _ in d_batches:
+            sym = lut[bytes_d.long()]
+            bitsm = ((sym[:, None] >> torch.arange(wire_bits, device=dev)[None, :]) & 1).reshape(-1)
+            pad = (-bitsm.numel()) % 8
+            if pad:
+                bitsm = torch.cat([bitsm, torch.zeros(pad, dtype=bitsm.dtype, device=dev)])
+            pk = (bitsm.reshape(-1, 8) * weights[None, :]).sum(1).to(torch.uint8)
+            hp = torch.empty(pk.numel(), dtype=torch.uint8).pin_memory()
+            hp.copy_(pk)
+            h_packed.append(hp)
+            del sym, bitsm, pk
+    h_outp = [torch.zeros(batch, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
+
     def e2e_run(nsteps, form):
         tickets = []
         for i in range(nsteps):
             hb, ho = h_batches[i % NB]
             if i >= DEPTH:
                 idx.count_batch_wait(tickets[i - DEPTH])  # frees output buffer i % DEPTH
-            if form == "len8":
+            if form == "packed":
+                tickets.append(idx.count_batch_submit_packed(h_packed[i % NB].data_ptr(), hb.numel(), h_lens8[i % NB].data_ptr(), batch,
+                                                             h_outp[i % DEPTH].data_ptr()))
+            elif form == "len8":
                 tickets.append(idx.count_batch_submit_len8(hb.data_ptr(), hb.numel(), h_lens8[i % NB].data_ptr(), batch,
                                                            h_out8[i % DEPTH].data_ptr()))
             elif form == "u32":
@@ -816,7 +839,7 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
 
     e2e_steps = args.steps
     e2e_times, e2e_bytes = {}, {}
-    for form in (("u64", "u32", "len8") if full else ("len8",)):
+    for form in (("u64", "u32", "len8") if full else ("len8",)) + (("packed",) if h_packed else ()):
         e2e_run(max(3, args.warmup), form)
         torch.cuda.synchronize()
         barrier()
@@ -854,6 +877,8 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
     step_device(e2e_steps - 1)  # same batch as the last end-to-end step: both paths must agree
     stream.synchronize()
     e2e_equal = bool((h_out8[last].numpy().astype(np.int64) == d_counts.cpu().numpy()).all())
+    if h_packed:
+        e2e_equal = e2e_equal and bool((h_outp[last].numpy().astype(np.int64) == d_counts.cpu().numpy()).all())
 
     # ---- the ceiling the e2e region is up against: the same bytes per step, copies only (all ranks at once) -------
     # pinned H2D of (lengths + pattern bytes) and pinned D2H of the u32 counts on two streams, no kernel
@@ -886,10 +911,12 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, e2e_s_u64, e2e_s_u32, copy_s or 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, e2e_s_u64, e2e_s_u32, copy_s or 0.0, e2e_times.get("packed", 0.0)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s, e2e_s_u64, e2e_s_u32 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         copy_s = float(t[4]) or None
+        if "packed" in e2e_times:
+            e2e_times["packed"] = float(t[5])
     if rank != 0:
         idx.close()
         del d_batches, h_batches, text
@@ -1031,6 +1058,13 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
            "api": "csfm_count_batch_submit_len8/_wait (host pointers, pinned, one length byte per pattern in, u32 counts "
                   "out, 3 steps in flight)",
            "kernels_per_step": 4}
+    if "packed" in e2e_times:
+        e2e["packed_api"] = {"value": world * e2e_steps * batch / e2e_times["packed"], "ms_per_step": 1e3 * e2e_times["packed"] / e2e_steps,
+                             "h2d_bytes_per_step": e2e_bytes["packed"][0], "d2h_bytes_per_step": e2e_bytes["packed"][1],
+                             "bits_per_symbol": wire_bits, "kernels_per_step": 5,
+                             "api": "csfm_count_batch_submit_packed/_wait (patterns as packed wire codes, one length byte per pattern in, u32 "
+                                    "counts out; codes unpacked on the device)",
+                             "note": "the copy ceiling below is for the byte form's traffic; this form moves fewer bytes per query"}
     if copy_s:
         ceil_v = world * e2e_steps * batch / copy_s
         e2e["copy_ceiling"] = {"value": ceil_v, "unit": "queries/s", "ms_per_step": 1e3 * copy_s / e2e_steps,

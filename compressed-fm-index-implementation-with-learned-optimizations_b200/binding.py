@@ -87,6 +87,8 @@ SIGNATURES = {
     "csfm_count_batch_submit": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_submit32": (C.c_int, [_vp, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_submit_len8": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
+    "csfm_pattern_codes": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint32)]),
+    "csfm_count_batch_submit_packed": (C.c_int, [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_count_batch_wait": (C.c_int, [_vp, C.c_uint64]),
     "csfm_locate_batch": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_locate_batch_device": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, _vp, C.c_uint64, _vp,
@@ -345,6 +347,27 @@ class FMIndex:
         t = C.c_uint64()
         _check(lib().csfm_count_batch_submit_len8(self._h, _vp(bytes_ptr), nbytes, _vp(lens8_ptr), npat, _vp(counts32_ptr),
                                                   C.byref(t)))
+        return int(t.value)
+
+    def pattern_codes(self):
+        """-> (code_of_byte u8[256], bits): the wire codes of csfm_count_batch_submit_packed."""
+        codes = np.zeros(256, np.uint8)
+        bits = C.c_uint32()
+        _check(lib().csfm_pattern_codes(self._h, _np_ptr(codes), C.byref(bits)))
+        return codes, int(bits.value)
+
+    def pack_codes(self, data) -> np.ndarray:
+        """Pattern bytes -> the packed wire form (LSB-first, `bits` per symbol, back to back)."""
+        codes, bits = self.pattern_codes()
+        sym = codes[np.ascontiguousarray(data, dtype=np.uint8)]
+        planes = ((sym[:, None] >> np.arange(bits, dtype=np.uint8)[None, :]) & 1).astype(np.uint8)
+        return np.packbits(planes.reshape(-1), bitorder="little")
+
+    def count_batch_submit_packed(self, packed_ptr: int, nsyms: int, lens8_ptr: int, npat: int, counts32_ptr: int) -> int:
+        """Smallest asynchronous count: packed wire codes + one length byte per pattern in, u32 counts out."""
+        t = C.c_uint64()
+        _check(lib().csfm_count_batch_submit_packed(self._h, _vp(packed_ptr), nsyms, _vp(lens8_ptr), npat, _vp(counts32_ptr),
+                                                    C.byref(t)))
         return int(t.value)
 
     def count_batch_wait(self, ticket: int):

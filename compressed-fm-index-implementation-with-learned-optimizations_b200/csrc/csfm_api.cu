@@ -658,8 +658,43 @@ __global__ void narrow_counts_kernel(const uint64_t* __restrict__ in, uint32_t* 
     out[i] = (uint32_t)in[i];
 }
 
+// packed wire codes -> pattern bytes: symbol i of the batch sits in bits [i * bits, (i + 1) * bits) of `packed`
+struct WireTable {
+  uint8_t byte_of_wire[256];
+};
+__global__ void unpack_codes_kernel(const uint8_t* __restrict__ packed, uint64_t packed_bytes, uint64_t nsyms, uint32_t bits,
+                                    const __grid_constant__ WireTable wt, uint8_t* __restrict__ out) {
+  const uint32_t mask = (1u << bits) - 1u;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nsyms; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t bit = i * bits, at = bit >> 3;
+    uint32_t w = packed[at];
+    if (at + 1 < packed_bytes) w |= (uint32_t)packed[at + 1] << 8;
+    out[i] = wt.byte_of_wire[(w >> (bit & 7)) & mask];
+  }
+}
+
+// wire codes of an index: the bytes that occur, in byte order; a code beyond them decodes to a byte that does not
+// occur (so the pattern counts 0), or — with all 256 bytes present — cannot be formed at all
+void wire_codes(const csfm_index* idx, uint8_t code_of_byte[256], uint8_t byte_of_wire[256], uint32_t* bits) {
+  uint32_t sigma = 0;
+  int absent = -1;
+  for (int c = 0; c < 256; ++c) {
+    if (idx->h.C[c + 1] != idx->h.C[c]) {
+      if (code_of_byte) code_of_byte[c] = (uint8_t)sigma;
+      byte_of_wire[sigma++] = (uint8_t)c;
+    } else {
+      if (code_of_byte) code_of_byte[c] = 255;
+      if (absent < 0) absent = c;
+    }
+  }
+  for (uint32_t k = sigma; k < 256; ++k) byte_of_wire[k] = (uint8_t)(absent < 0 ? 0 : absent);
+  uint32_t b = 1;
+  while ((1u << b) < sigma) ++b;
+  *bits = b;
+}
+
 // How a streaming batch describes where its patterns start.
-enum class PatternIndex { kOffsets64, kOffsets32, kLengths8 };
+enum class PatternIndex { kOffsets64, kOffsets32, kLengths8, kPackedLengths8 };
 
 // The three submit entry points differ only in how the pattern boundaries arrive and how wide the
 // counts leave: one slot, one stream, H2D copies -> (offsets rebuilt on the device) -> count kernel ->
@@ -679,8 +714,14 @@ int submit_batch(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes, Pattern
   const size_t offs_bytes = (npat + 1) * 8;
   const size_t bytes_at = (offs_bytes + 255) & ~(size_t)255;
   const size_t compact_at = (bytes_at + nbytes + 255) & ~(size_t)255;
-  const size_t compact_bytes = kind == PatternIndex::kOffsets32 ? (npat + 1) * 4 : kind == PatternIndex::kLengths8 ? npat + 1 : 0;
-  int rc = sl.in.ensure(compact_at + compact_bytes + 512);
+  const bool packed = kind == PatternIndex::kPackedLengths8;
+  uint32_t wire_bits = 8;
+  WireTable wt;
+  if (packed) wire_codes(idx, nullptr, wt.byte_of_wire, &wire_bits);
+  const uint64_t packed_bytes = packed ? (nbytes * wire_bits + 7) / 8 : 0;  // nbytes = symbols of the batch
+  const size_t compact_bytes = kind == PatternIndex::kOffsets32 ? (npat + 1) * 4 : (kind == PatternIndex::kLengths8 || packed) ? npat + 1 : 0;
+  const size_t packed_at = (compact_at + compact_bytes + 255) & ~(size_t)255;
+  int rc = sl.in.ensure(packed_at + packed_bytes + 512);
   if (rc) return rc;
   rc = sl.out.ensure(npat * 8 * (sp_ep ? 3 : 1) + (counts32 ? npat * 4 : 0));  // [counts u64][sp_ep][counts u32]
   if (rc) return rc;
@@ -703,16 +744,27 @@ int submit_batch(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes, Pattern
       idx->stats.h2d_bytes = (npat + 1) * 4 + nbytes;
       break;
     case PatternIndex::kLengths8:
+    case PatternIndex::kPackedLengths8:
       CSFM_CUDA(cudaMemcpyAsync(d_compact, index, npat, cudaMemcpyHostToDevice, sl.stream));
       CSFM_CUDA(cudaMemsetAsync(d_compact + npat, 0, 1, sl.stream));  // so that offs[npat] comes out of the same scan
-      idx->stats.h2d_bytes = npat + nbytes;
+      idx->stats.h2d_bytes = npat + (packed ? packed_bytes : nbytes);
       break;
   }
-  if (nbytes) CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  if (packed) {
+    uint8_t* d_packed = sl.in.as<uint8_t>() + packed_at;
+    if (packed_bytes) {
+      CSFM_CUDA(cudaMemcpyAsync(d_packed, bytes, packed_bytes, cudaMemcpyHostToDevice, sl.stream));
+      const int g = (int)std::min<uint64_t>((nbytes + 255) / 256, (uint64_t)idx->num_sms * 16);
+      unpack_codes_kernel<<<g, 256, 0, sl.stream>>>(d_packed, packed_bytes, nbytes, wire_bits, wt, d_bytes);
+      CSFM_CUDA(cudaGetLastError());
+    }
+  } else if (nbytes) {
+    CSFM_CUDA(cudaMemcpyAsync(d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, sl.stream));
+  }
   if (kind == PatternIndex::kOffsets32) {
     widen_offsets_kernel<<<grid, 256, 0, sl.stream>>>(reinterpret_cast<const uint32_t*>(d_compact), d_offs, npat + 1);
     CSFM_CUDA(cudaGetLastError());
-  } else if (kind == PatternIndex::kLengths8) {
+  } else if (kind == PatternIndex::kLengths8 || packed) {
     rc = offsets_from_lengths8(d_compact, npat + 1, d_offs, sl.scan, sl.stream);
     if (rc) return rc;
   }
@@ -761,6 +813,23 @@ int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t
   for (uint64_t i = 0; i < npat; ++i) sum += lens8[i];
   if (sum != nbytes) return fail(CSFM_ERR_INVALID, "nbytes differs from the sum of the pattern lengths");
   return submit_batch(idx, bytes, nbytes, PatternIndex::kLengths8, lens8, npat, nullptr, nullptr, counts32, ticket);
+}
+
+int csfm_pattern_codes(const csfm_index* idx, uint8_t code_of_byte[256], uint32_t* bits) {
+  if (!idx || !code_of_byte || !bits) return fail(CSFM_ERR_INVALID, "null argument");
+  uint8_t byte_of_wire[256];
+  wire_codes(idx, code_of_byte, byte_of_wire, bits);
+  return CSFM_OK;
+}
+
+int csfm_count_batch_submit_packed(csfm_index* idx, const uint8_t* packed, uint64_t nsyms, const uint8_t* lens8, uint64_t npat,
+                                   uint32_t* counts32, uint64_t* ticket) {
+  if (!idx || !ticket || (npat && (!lens8 || !counts32))) return fail(CSFM_ERR_INVALID, "null argument");
+  if (nsyms && !packed) return fail(CSFM_ERR_INVALID, "packed is null");
+  uint64_t sum = 0;  // the kernel trusts the rebuilt offsets: they must stay inside the unpacked symbols
+  for (uint64_t i = 0; i < npat; ++i) sum += lens8[i];
+  if (sum != nsyms) return fail(CSFM_ERR_INVALID, "nsyms differs from the sum of the pattern lengths");
+  return submit_batch(idx, packed, nsyms, PatternIndex::kPackedLengths8, lens8, npat, nullptr, nullptr, counts32, ticket);
 }
 
 int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket) {

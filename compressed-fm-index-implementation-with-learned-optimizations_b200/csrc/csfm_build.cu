@@ -406,6 +406,11 @@ int index_finish_handle(csfm_index* idx) {
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
+  v.kmer_entries = 0;
+  if (h.kmer_k) {
+    v.kmer_entries = 1;
+    for (uint32_t i = 0; i < h.kmer_k; ++i) v.kmer_entries *= h.kmer_radix;
+  }
   v.kmer_tiled = h.kmer_tiled;
   v.kmer_hi = (h.kmer_k && h.off_kmer_hi) ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer_hi) : nullptr;
   if (std::getenv("CSFM_NO_HALF_TABLE")) v.kmer_hi = nullptr;  // experiment knob: ignore a table that is present

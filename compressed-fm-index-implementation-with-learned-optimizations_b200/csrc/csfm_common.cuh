@@ -34,6 +34,7 @@
 // start always descends from 0, so it folds into the per-symbol constant base[c].
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace csfm {
@@ -134,11 +135,29 @@ struct IndexView {
   uint32_t refill_wait;  // ... or this many trips after its last refill, whichever comes first
   uint32_t special_first;  // layout 3: C[special byte] = the row LF maps special_row to
   uint32_t special_byte;
+  uint64_t kmer_entries;   // keys of the k-mer table (radix ^ k), 0 = no table
   uint32_t zeros[kMaxLevels];
 };
 
 // ---- device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Debug build (-DCSFM_BOUNDS_CHECK, tools/bounds_check.py: the stand-in for compute-sanitizer, which is closed on the GPU
+// pool): every data-dependent address the query kernels form — level lines, table entries, suffix-array entries, text
+// windows, pattern bytes — is checked against the extent of its section before the load; a violation prints and
+// traps, so the launch (and the test) fails instead of reading a neighbour's bytes. Compiles to nothing otherwise.
+#ifdef CSFM_BOUNDS_CHECK
+#define CSFM_CHK(cond, what)                                                                     \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      printf("CSFM_BOUNDS_CHECK: %s violated at %s:%d (block %d thread %d)\n", what, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                 \
+      __trap();                                                                                  \
+    }                                                                                            \
+  } while (0)
+#else
+#define CSFM_CHK(cond, what) ((void)0)
+#endif
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
@@ -242,6 +261,14 @@ __device__ __forceinline__ bool row_is_sampled(const IndexView& iv, uint32_t row
 }
 __device__ __forceinline__ uint32_t sample_index(const IndexView& iv, uint32_t row) {
   return iv.stride_shift < 32 ? row >> iv.stride_shift : row / iv.stride;
+}
+
+// a `bytes`-byte load at `p` must lie inside the level lines of the index
+__device__ __forceinline__ void check_line(const IndexView& iv, const void* p, uint32_t bytes) {
+  CSFM_CHK(reinterpret_cast<const uint8_t*>(p) >= iv.levels &&
+               reinterpret_cast<const uint8_t*>(p) + bytes <= iv.levels + (uint64_t)iv.L * iv.level_stride,
+           "level line inside the index");
+  (void)iv; (void)p; (void)bytes;
 }
 
 __device__ __forceinline__ uint32_t group4_sum(uint32_t v) {

@@ -37,13 +37,13 @@ namespace {
 
 // rank_l(v, sp) and rank_l(v, ep) for one level. lv = level base + 32*j. All 32 lanes call it.
 __device__ __forceinline__ void rank_pair(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp_pos, uint32_t ep_pos,
-                                          bool active, int j, uint32_t& rs, uint32_t& re) {
+                                          bool active, int j, uint32_t& rs, uint32_t& re, const IndexView& iv) {
   const uint32_t ls = sp_pos & ~(kSymsPerLine - 1), le = ep_pos & ~(kSymsPerLine - 1);  // line*128 == byte offset
   const uint32_t os = sp_pos - ls, oe = ep_pos - le;
   const bool split = active && (le != ls);
   Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
-  if (active) ks = ldg_nc_v8(lv + ls);
-  if (split) ke = ldg_nc_v8(lv + le);
+  if (active) { check_line(iv, lv + ls, 32); ks = ldg_nc_v8(lv + ls); }
+  if (split) { check_line(iv, lv + le, 32); ke = ldg_nc_v8(lv + le); }
   const uint32_t hs = chunk_hits(ks, v);
   const uint32_t cs = chunk_counter(ks, v, j);
   uint32_t he = hs, ce = cs;
@@ -155,6 +155,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
       q = a.qlist ? a.qlist[item] : item;
       const uint64_t o0 = a.offs[q], o1 = a.offs[(uint64_t)q + 1];
       const uint64_t m = o1 - o0;
+      CSFM_CHK(q < a.npat && o0 <= o1 && o1 <= a.offs[a.npat], "pattern inside the batch");
       active = true;
       if (m == 0) {
         // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
@@ -183,6 +184,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           ptr = a.bytes + (o1 - 1 - kk);
           rem = (uint32_t)(m - kk);
           const uint4 st = step_tab[*ptr];
+          CSFM_CHK(!present || e < iv.kmer_entries, "k-mer key inside the table");
           if (present && !(st.y & 0x80000000u)) se = kmer_hi[(size_t)e * 16u + (st.y >> 4)];
           sp = se.x;
           ep = se.y;
@@ -196,6 +198,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
             pre = true;
           }
         } else {
+          CSFM_CHK(!present || e < iv.kmer_entries, "k-mer key inside the table");
           if (present) {
             if (iv.kmer_tiled) {  // sp only: the next key's sp is this key's ep
               const uint32_t* const t = reinterpret_cast<const uint32_t*>(iv.kmer);
@@ -216,6 +219,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
             if (shortcut && ep - sp <= max_rows && rem >= iv.verify_min && rem <= kVerifyMax && (sp & dense_mask) == 0) {
               // a long table key already leaves few rows: verify them without a rank step
               next_byte = ptr[-1];
+              CSFM_CHK(ep <= iv.n, "interval inside the suffix array");
               if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
               vstage = 1;
               if (kInstr) ++my_checks;
@@ -279,7 +283,10 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           if (r == 0 || __any_sync(0xFFFFFFFFu, stage_ok && r < rows)) {
             const uint32_t tal = (vr - rem) & ~15u;
             const uint32_t nt16 = (vr - tal + 15) >> 4;
-            if (stage_ok && r < rows && (uint32_t)j < nt16) cp_async16(&vs.t[r][16 * j], iv.text + tal + 16 * j);
+            if (stage_ok && r < rows && (uint32_t)j < nt16) {
+              CSFM_CHK(vr <= iv.n && vr >= rem && (uint64_t)tal + 16 * j + 16 <= (uint64_t)iv.n + 64, "text window inside the text section");
+              cp_async16(&vs.t[r][16 * j], iv.text + tal + 16 * j);
+            }
           }
         }
         if (vstage == 1) {
@@ -302,14 +309,14 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     uint32_t rs, re, s1 = sp, e1 = ep;  // sp and ep themselves must survive a trip spent in verification
     if (two && (!kShortcut || __any_sync(0xFFFFFFFFu, ranking && !pre))) {
       if (kInstr && ranking && !pre) my_lines += 1u + (((sp ^ ep) >> 7) != 0u);
-      rank_pair(lv0, code >> 4, sp, ep, ranking && !pre, j, rs, re);
+      rank_pair(lv0, code >> 4, sp, ep, ranking && !pre, j, rs, re, iv);
       if (!pre) {
         s1 = add0 + rs;
         e1 = add0 + re;
       }
     }
     if (kInstr && ranking) my_lines += 1u + (((s1 ^ e1) >> 7) != 0u);
-    rank_pair(lv_last, code & 15u, s1, e1, ranking, j, rs, re);
+    rank_pair(lv_last, code & 15u, s1, e1, ranking, j, rs, re, iv);
     if (ranking) {
       pre = false;
       sp = base + rs;  // fm_index.cpp:92-93
@@ -322,6 +329,7 @@ count2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         // Few rows left: the suffix of row r starts at SA[r], and r stays in the interval iff the
         // rem characters before that text position equal the rest of the pattern. Ask for the
         // suffix-array entries now (lane j: row sp + j), use them next trip.
+        CSFM_CHK(ep <= iv.n, "interval inside the suffix array");
         if ((uint32_t)j < ep - sp) vp = iv.dense[(sp >> iv.dense_shift) + j];
         vstage = 1;
         if (kInstr) ++my_checks;
@@ -600,11 +608,11 @@ kmer_build_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tabl
       const bool act = alive && (tb.C[byte + 1] != tb.C[byte]);
       uint32_t rs, re;
       if (two) {
-        rank_pair(lv0, code >> 4, sp, ep, act, j, rs, re);
+        rank_pair(lv0, code >> 4, sp, ep, act, j, rs, re, iv);
         sp = tb.start1[code >> 4] + rs;
         ep = tb.start1[code >> 4] + re;
       }
-      rank_pair(lv_last, code & 15u, sp, ep, act, j, rs, re);
+      rank_pair(lv_last, code & 15u, sp, ep, act, j, rs, re, iv);
       sp = tb.base_by_code[code] + rs;
       ep = tb.base_by_code[code] + re;
       alive = act && sp < ep;
@@ -879,11 +887,11 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
     // ---- C. one backward-search step: sp/ep <- base[c] + rank_last(lo, start1[hi] + rank_0(hi, .))
     uint32_t rs, re;
     if (two) {
-      rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re);
+      rank_pair(lv0, code >> 4, sp, ep, active, j, rs, re, iv);
       sp = add0 + rs;
       ep = add0 + re;
     }
-    rank_pair(lv_last, code & 15u, sp, ep, active, j, rs, re);
+    rank_pair(lv_last, code & 15u, sp, ep, active, j, rs, re, iv);
     if (active) {
       sp = base + rs;  // fm_index.cpp:92-93
       ep = base + re;
@@ -969,11 +977,11 @@ count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant
       if (x.y & 0x80000000u) { alive = false; break; }
       uint32_t rs, re, s1 = sp, e1 = ep;
       if (two) {
-        rank_pair(lv0, (x.y & 0xFFu) >> 4, sp, ep, mine, j, rs, re);
+        rank_pair(lv0, (x.y & 0xFFu) >> 4, sp, ep, mine, j, rs, re, iv);
         s1 = x.z + rs;
         e1 = x.z + re;
       }
-      rank_pair(lv_last, x.y & 15u, s1, e1, mine, j, rs, re);
+      rank_pair(lv_last, x.y & 15u, s1, e1, mine, j, rs, re, iv);
       sp = __shfl_sync(0xFFFFFFFFu, x.x + rs, 0);
       ep = __shfl_sync(0xFFFFFFFFu, x.x + re, 0);
       alive = sp < ep;
@@ -993,10 +1001,10 @@ count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant
 // One level of access(p) fused with rank (both read the same line): returns the symbol at p in
 // `v` and rank_l(v, p) as the function value. All 32 lanes must call it (shuffles).
 __device__ __forceinline__ uint32_t access_rank_level(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane,
-                                                      int j, uint32_t& v) {
+                                                      int j, uint32_t& v, const IndexView& iv) {
   Chunk32 k = chunk_undefined();
   const uint32_t line = p & ~(kSymsPerLine - 1), off = p - line;
-  if (active) k = ldg_nc_v8(lv + line);
+  if (active) { check_line(iv, lv + line, 32); k = ldg_nc_v8(lv + line); }
   v = __shfl_sync(0xFFFFFFFFu, chunk_symbol(k, off), (lane & ~3) | (int)(off >> 5));
   return group4_sum(chunk_partial(chunk_counter(k, v, j), chunk_hits(k, v), off, j));
 }
@@ -1061,10 +1069,10 @@ walk2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
 
     // ---- one LF step: LF(i) = C[c] + occ(c,i) = base[c] + rank_last(lo, .)  (fm_index.hpp:62-66)
     uint32_t v, code = 0;
-    uint32_t r = access_rank_level(lv0, p, active, lane, j, v);
+    uint32_t r = access_rank_level(lv0, p, active, lane, j, v, iv);
     if (two) {
       code = v << 4;
-      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v);
+      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v, iv);
     }
     code |= v;
     if (active) {
@@ -1119,10 +1127,10 @@ untext2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, 
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
     uint32_t v, code = 0;
-    uint32_t r = access_rank_level(lv0, p, active, lane, j, v);
+    uint32_t r = access_rank_level(lv0, p, active, lane, j, v, iv);
     if (two) {
       code = v << 4;
-      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v);
+      r = access_rank_level(lv1, tb.start1[v] + r, active, lane, j, v, iv);
     }
     code |= v;
     if (active) {
@@ -1157,11 +1165,11 @@ access2_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
     const uint64_t i = t * ngroups + group;
     const bool valid = i < iv.n;
     uint32_t v;
-    uint32_t r = access_rank_level(lv0, valid ? (uint32_t)i : 0u, valid, lane, j, v);
+    uint32_t r = access_rank_level(lv0, valid ? (uint32_t)i : 0u, valid, lane, j, v, iv);
     uint32_t code = v;
     if (two) {
       const uint32_t hi = v;
-      r = access_rank_level(lv1, tb.start1[hi] + r, valid, lane, j, v);
+      r = access_rank_level(lv1, tb.start1[hi] + r, valid, lane, j, v, iv);
       code = (hi << 4) | v;
     }
     if (valid && j == 0) out[i] = tb.byte_of_code[code];

@@ -21,15 +21,15 @@ namespace {
 // rank(v, sp) and rank(v, ep) in the one level of the index. lv = level base + 32 * h. All 32 lanes call it.
 // v == kSpecialCode (the symbol that occurs once, at BWT row px): occ(v, p) = (p > px), no memory access.
 __device__ __forceinline__ void rank_pair3(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp, uint32_t ep, bool active,
-                                           int h, uint32_t px, uint32_t& rs, uint32_t& re) {
+                                           int h, uint32_t px, uint32_t& rs, uint32_t& re, const IndexView& iv) {
   const bool special = v == kSpecialCode;
   const uint32_t ls = dna_line_of(sp), le = dna_line_of(ep);
   const uint32_t os = sp - ls * kSymsPerLine3, oe = ep - le * kSymsPerLine3;
   const bool load = active && !special;
   const bool split = load && (le != ls);
   Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
-  if (load) ks = ldg_nc_v8(lv + (size_t)ls * kLine3Bytes);
-  if (split) ke = ldg_nc_v8(lv + (size_t)le * kLine3Bytes);
+  if (load) { check_line(iv, lv + (size_t)ls * kLine3Bytes, 32); ks = ldg_nc_v8(lv + (size_t)ls * kLine3Bytes); }
+  if (split) { check_line(iv, lv + (size_t)le * kLine3Bytes, 32); ke = ldg_nc_v8(lv + (size_t)le * kLine3Bytes); }
   DnaHits xs = dna_hits(ks, v);
   const uint32_t cs = dna_counter(ks, v, h);
   const uint32_t ps = dna_partial(cs, xs, os, h);
@@ -114,6 +114,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
       q = item;
       const uint64_t o0 = a.offs[q], o1 = a.offs[(uint64_t)q + 1];
       const uint64_t m = o1 - o0;
+      CSFM_CHK(q < a.npat && o0 <= o1 && o1 <= a.offs[a.npat], "pattern inside the batch");
       active = true;
       if (m == 0) {
         // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
@@ -143,6 +144,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
           finish(0, 0, 0);
         } else if (keyed) {
           if (kInstr) ++my_lookups;
+          CSFM_CHK(e < iv.kmer_entries, "k-mer key inside the table");
           const uint2 se = iv.kmer[e];
           sp = se.x;
           ep = se.y;
@@ -178,7 +180,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // ---- one backward-search step: sp/ep <- C[c] + rank(c, .)  (fm_index.cpp:92-93)
     if (kInstr && active && code != kSpecialCode) my_lines += 1u + (dna_line_of(sp) != dna_line_of(ep) ? 1u : 0u);
     uint32_t rs, re;
-    rank_pair3(lv, code, sp, ep, active, h, px, rs, re);
+    rank_pair3(lv, code, sp, ep, active, h, px, rs, re, iv);
     if (active) {
       sp = base + rs;
       ep = base + re;
@@ -235,7 +237,7 @@ kmer_build3_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tab
       byte = byte_of_code[code];
       const bool act = alive && (sC[byte + 1] != sC[byte]);
       uint32_t rs, re;
-      rank_pair3(lv, code, sp, ep, act, h, px, rs, re);
+      rank_pair3(lv, code, sp, ep, act, h, px, rs, re, iv);
       sp = sC[byte] + rs;
       ep = sC[byte] + re;
       alive = act && sp < ep;
@@ -246,10 +248,10 @@ kmer_build3_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tab
 
 // One LF step's memory access: the symbol at row p and its rank before p, from ONE line.
 __device__ __forceinline__ uint32_t access_rank3(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane, int h,
-                                                 uint32_t& v) {
+                                                 uint32_t& v, const IndexView& iv) {
   Chunk32 k = chunk_undefined();
   const uint32_t line = dna_line_of(p), off = p - line * kSymsPerLine3;
-  if (active) k = ldg_nc_v8(lv + (size_t)line * kLine3Bytes);
+  if (active) { check_line(iv, lv + (size_t)line * kLine3Bytes, 32); k = ldg_nc_v8(lv + (size_t)line * kLine3Bytes); }
   v = __shfl_sync(0xFFFFFFFFu, dna_symbol(k, off, h), (lane & ~1) | (off >= 96u ? 1 : 0));
   return group2_sum(dna_partial(dna_counter(k, v, h), dna_hits(k, v), off, h));
 }
@@ -292,6 +294,7 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
       fail_walk((int)CSFM_Q_SSA_OOB);
       return;
     }
+    CSFM_CHK(k < iv.nsamp, "sample index inside the sampled suffix array");
     if (h == 0) {
       uint64_t pos = (uint64_t)iv.ssa[k] + steps;  // fm_index.cpp:147-152
       if (pos >= iv.n) pos -= iv.n;                // sa_val < n and steps < n
@@ -314,7 +317,7 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
 
     // ---- one LF step: LF(i) = C[c] + occ(c, i)  (fm_index.hpp:62-66)
     uint32_t v;
-    const uint32_t r = access_rank3(lv, p, active, lane, h, v);
+    const uint32_t r = access_rank3(lv, p, active, lane, h, v, iv);
     if (active) {
       // row px holds the symbol that occurs once: LF(px) = C[that symbol] + 0
       const uint32_t row = p == px ? iv.special_first : base_by_code[v] + r - ((v == 0u && p > px) ? 1u : 0u);
@@ -366,7 +369,7 @@ untext3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, 
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
     uint32_t v;
-    const uint32_t r = access_rank3(lv, p, active, lane, h, v);
+    const uint32_t r = access_rank3(lv, p, active, lane, h, v, iv);
     if (active) {
       pos = pos == 0 ? iv.n - 1 : pos - 1;  // BWT[row] = T[(SA[row] - 1) mod n]  (bwt.hpp:10-13)
       if (h == 0) out[pos] = p == px ? (uint8_t)iv.special_byte : byte_of_code[v];
@@ -398,7 +401,7 @@ access3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
     const uint64_t i = t * ngroups + group;
     const bool valid = i < iv.n;
     uint32_t v;
-    (void)access_rank3(lv, valid ? (uint32_t)i : 0u, valid, lane, h, v);
+    (void)access_rank3(lv, valid ? (uint32_t)i : 0u, valid, lane, h, v, iv);
     if (valid && h == 0) out[i] = (uint32_t)i == iv.special_row ? (uint8_t)iv.special_byte : byte_of_code[v];
   }
 }

@@ -223,6 +223,15 @@ CSFM_API int csfm_count_batch_submit32(csfm_index* idx, const uint8_t* bytes, co
 CSFM_API int csfm_count_batch_submit_len8(csfm_index* idx, const uint8_t* bytes, uint64_t nbytes,
                                           const uint8_t* lens8, uint64_t npat, uint32_t* counts32,
                                           uint64_t* ticket);
+/* Smallest form on the wire, for small alphabets (DNA: 3 bits per symbol instead of 8): patterns travel as the index's
+ * WIRE CODES — csfm_pattern_codes gives code_of_byte[] (0 .. sigma-1 for the bytes that occur, in byte order; 255 for
+ * bytes that do not) and `bits` = max(1, ceil(log2 sigma)) — packed LSB-first back to back across pattern boundaries:
+ * symbol i of the batch occupies bits [i * bits, (i + 1) * bits) of `packed` (ceil(nsyms * bits / 8) bytes). One length
+ * byte per pattern as in the len8 form; nsyms must equal the sum of the lengths. A code >= sigma stands for a symbol
+ * that does not occur (the pattern counts 0). The codes are unpacked to bytes on the device by one extra kernel. */
+CSFM_API int csfm_pattern_codes(const csfm_index* idx, uint8_t code_of_byte[256], uint32_t* bits);
+CSFM_API int csfm_count_batch_submit_packed(csfm_index* idx, const uint8_t* packed, uint64_t nsyms, const uint8_t* lens8,
+                                            uint64_t npat, uint32_t* counts32, uint64_t* ticket);
 CSFM_API int csfm_count_batch_wait(csfm_index* idx, uint64_t ticket);
 CSFM_API int csfm_count_batch_device(csfm_index* idx, const uint8_t* d_bytes,
                                      const uint64_t* d_offs, uint64_t npat, uint64_t* d_counts,

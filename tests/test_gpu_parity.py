@@ -296,6 +296,38 @@ def test_extract_needs_a_terminated_text(fm):
         lay1.extract(0, 3)
 
 
+@pytest.mark.parametrize("sigma,n", [(4, 120_000), (2, 9_000), (1, 500), (20, 60_000), (255, 80_000)])
+def test_async_submit_packed_codes(fm, sigma, n):
+    """csfm_count_batch_submit_packed: patterns as packed wire codes (3 bits per symbol for DNA + terminator)."""
+    rng = np.random.default_rng(sigma * 31 + n)
+    text, alpha = _rand_text(rng, n, sigma, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16))
+    orc = oracle.OracleIndex(text, stride=16)
+    codes, bits = idx.pattern_codes()
+    present = np.unique(text)
+    assert bits == max(1, int(np.ceil(np.log2(present.size)))) and (codes[present] == np.arange(present.size)).all()
+    pats = [p for p in _mixed_patterns(rng, text, alpha, 5000, 40) if len(p) <= 255 and all(codes[b] != 255 for b in p)]
+    pats += [b"", text[-3:].tobytes()]
+    d, o = fm.pack_patterns(pats)
+    oc, _ = orc.count_batch(d, o)
+    packed = idx.pack_codes(d)
+    assert packed.size == (d.size * bits + 7) // 8
+    lens = np.diff(o).astype(np.uint8)
+    out = np.zeros(len(pats), np.uint32)
+    t = idx.count_batch_submit_packed(packed.ctypes.data, d.size, lens.ctypes.data, len(pats), out.ctypes.data)
+    idx.count_batch_wait(t)
+    assert (out.astype(np.uint64) == oc).all()
+    # a code beyond the alphabet stands for a symbol that does not occur: count 0
+    if present.size < (1 << bits):
+        bad = np.packbits(((np.full(4, (1 << bits) - 1)[:, None] >> np.arange(bits)[None, :]) & 1).astype(np.uint8).reshape(-1), bitorder="little")
+        out1 = np.full(1, 7, np.uint32)
+        l1 = np.array([4], np.uint8)
+        idx.count_batch_wait(idx.count_batch_submit_packed(bad.ctypes.data, 4, l1.ctypes.data, 1, out1.ctypes.data))
+        assert out1[0] == 0
+    with pytest.raises(fm.CsfmError, match="sum of the pattern lengths"):
+        idx.count_batch_submit_packed(packed.ctypes.data, d.size + 1, lens.ctypes.data, len(pats), out.ctypes.data)
+
+
 def test_host_offsets_are_checked(fm):
     idx = fm.FMIndex.build_from_text(b"mississippi$", fm.BuildParams(ssa_stride=4))
     d = np.frombuffer(b"ssiissi", np.uint8)
