@@ -1276,10 +1276,13 @@ def run_engine(args, rank, world, local_rank):
         c2 = guarded("c2", lambda: count_leg(sub, "c2", rank, world, local_rank, min(args.steps, 100), 5, full=False))
         if rank == 0:
             configs["c1"] = guarded("c1", lambda: leg_c1(local_rank, args.cpu_budget if cpu_ok else 0.0))
+        free_gb = torch.cuda.mem_get_info()[0] / 1e9
         if world > 1:
             import torch.distributed as dist
-            dist.barrier()
-        free_gb = torch.cuda.mem_get_info()[0] / 1e9
+            # every rank must take the same branch below (the leg has collectives): decide on the minimum
+            fmin = torch.tensor([free_gb], dtype=torch.float64, device=dev)
+            dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
+            free_gb = float(fmin[0])
         if free_gb > 150:
             c5_steps = max(3, -(-100 // world))  # the 100 M-pattern sweep of the config, split over the ranks
             c5 = guarded("c5", lambda: count_leg(sub, "c5", rank, world, local_rank, c5_steps, 3, full=False))
