@@ -65,8 +65,14 @@ __device__ __forceinline__ uint32_t dna_partial(uint32_t cnt, const DnaHits& x, 
 __device__ __forceinline__ uint32_t dna_symbol(const Chunk32& k, uint32_t off, int h) {
   const uint32_t loff = off - 96u * (uint32_t)h;  // 0..95 in the owning lane
   const uint32_t t = loff >> 5, s = loff & 31u;
+#ifdef CSFM_DNA_SYMBOL_BRANCHY
   const uint32_t lo = t == 0 ? k.c2 : (t == 1 ? k.p0 : k.p2);
   const uint32_t hi = t == 0 ? k.c3 : (t == 1 ? k.p1 : k.p3);
+#else
+  // selp chains (the ternary form compiles to divergent branches); in the other lane t is garbage: only its low bits are looked at
+  const uint32_t lo = pick4(k.c2, k.p0, k.p2, k.p2, t);
+  const uint32_t hi = pick4(k.c3, k.p1, k.p3, k.p3, t);
+#endif
   return ((lo >> s) & 1u) | (((hi >> s) & 1u) << 1);
 }
 __device__ __forceinline__ uint32_t group2_sum(uint32_t v) { return v + __shfl_xor_sync(0xFFFFFFFFu, v, 1); }
