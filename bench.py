@@ -454,6 +454,12 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
     t_s = ms / 1e3
     kname = {1: "walk_kernel", 2: "walk2_kernel", 3: "walk3_kernel"}.get(int(info.layout), "walk_kernel")
     traffic, tmeta = committed_traffic("c4_walk", kname)
+    if traffic and tmeta.get("units_per_launch"):
+        # the capture is of a smaller batch: DRAM bytes per occurrence x this batch's occurrences (per GPU)
+        traffic = traffic / float(tmeta["units_per_launch"]) * (total_all / world)
+        tmeta["scaled_to_occurrences"] = total_all / world
+    elif traffic:
+        traffic, tmeta = None, {"valid": False, "why": "capture does not say how many occurrences it walked"}
     in_l2 = int(info.blob_bytes) <= L2_RESIDENT_BYTES
     ws_peak, ws_src = l2_random_peak(int(info.blob_bytes), lb)
     achieved_exec = alg / world / t_s / 1e9
@@ -1000,7 +1006,7 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
         roofline["stepping_only"] = stepping
     if large:
         if "achieved_gbs" in large:
-            t3, t3_meta = committed_traffic(args.workload + "_large_table", "count2q_kernel")
+            t3, t3_meta = committed_traffic(args.workload + "_large_table", "count2_kernel<true,false>")
             tl = large["ms_per_launch"] / 1e3
             pe = large["level_lines_fetched_per_launch"] * line_bytes + large["table_lookups_per_launch"] * 128 + large["text_checks_per_launch"] * 256
             large.update({"executed_bytes_per_launch": pe, "traffic": t3, "traffic_capture": t3_meta,

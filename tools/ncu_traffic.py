@@ -3,7 +3,8 @@
 (dram__bytes_read.sum + dram__bytes_write.sum), the kernel it is of, and a few memory-system metrics — stamped with
 a hash of the kernel sources so that bench.py only uses a capture that belongs to the code it is running.
 
-usage: tools/ncu_traffic.py key=report.ncu-rep[:kernel-substring] ...      (keys: c3, c3_stepping, c3_large_table, c2, c5, c4_walk)
+usage: tools/ncu_traffic.py key=report.ncu-rep[:kernel-substring[:units]] ...      (keys: c3, c3_stepping, c3_large_table, c2, c5, c4_walk)
+`units` (optional) = work items of the captured launch (occurrences of the walk): bench.py scales the bytes to its own batch.
 """
 import csv
 import io
@@ -67,8 +68,11 @@ def main():
     out = {"source_sha16": sources_sha16(), "generator": "tools/ncu_traffic.py", "captures": {}}
     for arg in sys.argv[1:]:
         key, rest = arg.split("=", 1)
-        path, _, want = rest.partition(":")
+        parts = rest.split(":")
+        path, want = parts[0], parts[1] if len(parts) > 1 else ""
         out["captures"][key] = read_report(path, want)
+        if len(parts) > 2:
+            out["captures"][key]["units_per_launch"] = int(parts[2])
     json.dump(out, open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 
