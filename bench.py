@@ -963,11 +963,15 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
     else:
         basis = "dram traffic (ncu) / duration" if traffic else "executed line fetches x 128 B / duration (no valid ncu capture for these sources)"
         achieved = (traffic if traffic else executed_bytes) / t_launch_s / 1e9
+        # the ceiling that binds: dependent random fetches per second out of HBM, for this line size (128-byte lines:
+        # profiles/r1_gather_probe.json; 64-byte lines: the 1 GiB row of profiles/r2_l2_sweep_probe.json)
+        fetch_ceiling = RANDOM_FETCH_CEILING if line_bytes == 128 else l2_random_peak(1 << 30, line_bytes)[0] * 1e9 / line_bytes
+        fetches = (lines_m + lookups_m + 2 * checks_m) if have_lines else executed_bytes / line_bytes
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "frac_basis": basis,
-                    "line_fetches_per_s": (traffic if traffic else executed_bytes) / 128 / t_launch_s,
-                    "random_fetch_ceiling_lines_per_s": RANDOM_FETCH_CEILING,
-                    "frac_of_random_fetch_ceiling": (traffic if traffic else executed_bytes) / 128 / t_launch_s / RANDOM_FETCH_CEILING}
+                    "line_fetches_per_s": fetches / t_launch_s,
+                    "random_fetch_ceiling_lines_per_s": fetch_ceiling,
+                    "frac_of_random_fetch_ceiling": fetches / t_launch_s / fetch_ceiling}
     roofline.update({
         "traffic_capture": traffic_meta,
         "model": {"bytes_per_launch": model_bytes, "gbs": model_bytes / t_launch_s / 1e9, "frac_of_hbm_peak": model_bytes / t_launch_s / 1e9 / peak,
