@@ -845,14 +845,18 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
 
     e2e_steps = args.steps
     e2e_times, e2e_bytes = {}, {}
+    e2e_clock_samples, e2e_clock_reasons = [], set()
     for form in (("u64", "u32", "len8") if full else ("len8",)) + (("packed",) if h_packed else ()):
         e2e_run(max(3, args.warmup), form)
         torch.cuda.synchronize()
         barrier()
-        t0 = time.perf_counter()
-        e2e_run(e2e_steps, form)
-        torch.cuda.synchronize()
-        e2e_times[form] = time.perf_counter() - t0
+        with ClockSampler(local_rank) as clocks_e2e_form:  # the e2e regions last longer: more clock samples under load
+            t0 = time.perf_counter()
+            e2e_run(e2e_steps, form)
+            torch.cuda.synchronize()
+            e2e_times[form] = time.perf_counter() - t0
+        e2e_clock_samples.extend(clocks_e2e_form.samples)
+        e2e_clock_reasons |= clocks_e2e_form.reasons
         barrier()
         stf = idx.last_call_stats()
         e2e_bytes[form] = (int(stf.h2d_bytes), int(stf.d2h_bytes))
@@ -1109,7 +1113,8 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "construction": construction,
-        "clocks": clocks.summary(),
+        "clocks": dict(clocks.summary(), e2e_regions={"sm_mhz": float(np.median(e2e_clock_samples)) if e2e_clock_samples else None,
+                                                      "samples": len(e2e_clock_samples), "reasons": sorted(e2e_clock_reasons)}),
         "checks": {"all_counts_ge_1": True, "e2e_equals_device": e2e_equal, "compact_equals_u64_api": compact_equal,
                    "naive_text_scan_equals_counts": naive_ok,
                    "bit_exact_vs_reference_sample": (cpu or {}).get("bit_exact_vs_gpu")},

@@ -79,6 +79,7 @@ SIGNATURES = {
     "csfm_extract": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, C.POINTER(C.c_uint64)]),
     "csfm_blob": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
     "csfm_attach_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "csfm_alias": (C.c_int, [_vp, C.POINTER(_vp)]),
     "csfm_replicate": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "csfm_blob_to_host": (C.c_int, [_vp, _vp, C.c_uint64]),
     "csfm_from_host_blob": (C.c_int, [_vp, C.c_uint64, C.c_int, C.POINTER(_vp)]),
@@ -202,6 +203,15 @@ class FMIndex:
         idx = FMIndex(h)
         idx._keepalive = keepalive
         return idx
+
+    def alias(self) -> "FMIndex":
+        """A second handle over the same device blob (no copy) for another host thread (csfm_alias). Keeps this
+        handle alive for as long as the alias lives."""
+        h = _vp()
+        _check(lib().csfm_alias(self._h, C.byref(h)))
+        a = FMIndex(h, text=self._text)
+        a._keepalive = self
+        return a
 
     def replicate(self, device: int) -> "FMIndex":
         """A second handle over its own copy of the blob on `device` (csfm_replicate)."""

@@ -442,6 +442,22 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   return CSFM_OK;
 }
 
+// A second handle over the SAME device blob (no copy): its own streams, workspaces, statistics and mutex, so that
+// another host thread can query the index concurrently. The alias borrows the blob: destroy it before the handle
+// that owns the blob.
+int csfm_alias(const csfm_index* idx, csfm_index** out) {
+  if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
+  const int rc = csfm_attach_blob(idx->d_blob, idx->blob_bytes, idx->device, 0, out);
+  if (rc == CSFM_OK) {
+    (*out)->instr_mask = 0;
+    (*out)->tma_staging = idx->tma_staging;
+    (*out)->no_two_pass = idx->no_two_pass;
+    (*out)->no_sa_locate = idx->no_sa_locate;
+    (*out)->view = idx->view;  // the same experiment knobs as the handle it aliases
+  }
+  return rc;
+}
+
 int csfm_replicate(const csfm_index* idx, int device, csfm_index** out) {
   if (!idx || !out) return fail(CSFM_ERR_INVALID, "null argument");
   *out = nullptr;

@@ -46,6 +46,25 @@ void pack(const std::vector<std::string_view>& pats, std::vector<uint8_t>& bytes
 
 void FMIndex::set_default_device(int device) { g_default_device = device; }
 
+csfm_index* FMIndex::local() const {
+  if (!handle_ || std::this_thread::get_id() == owner_) return handle_.get();
+  // a few aliases per thread, most recently used first; an entry keeps the index that owns the blob alive
+  struct Entry {
+    std::shared_ptr<csfm_index> owner, alias;
+  };
+  static thread_local std::vector<Entry> cache;
+  for (size_t i = 0; i < cache.size(); ++i)
+    if (cache[i].owner.get() == handle_.get()) {
+      if (i) std::swap(cache[i], cache[0]);
+      return cache[0].alias.get();
+    }
+  csfm_index* a = nullptr;
+  if (csfm_alias(handle_.get(), &a) != CSFM_OK) return handle_.get();  // still correct, only serialised
+  if (cache.size() >= 4) cache.pop_back();
+  cache.insert(cache.begin(), Entry{handle_, std::shared_ptr<csfm_index>(a, [](csfm_index* x) { csfm_destroy(x); })});
+  return a;
+}
+
 FMIndex FMIndex::build_from_text(const std::string& text, const BuildParams& p) {
   return build_from_text(text, p, CSFM_BUILD_DEFAULT);
 }
@@ -104,7 +123,9 @@ void FMIndex::count_batch_sharded(const std::vector<FMIndex>& replicas, const ui
         // a slice keeps the batch's absolute offsets: rebase them so that the slice is a batch of its own
         std::vector<uint64_t> local(hi - lo + 1);
         for (uint64_t i = lo; i <= hi; ++i) local[i - lo] = offs[i] - offs[lo];
-        replicas[r].count_batch(bytes + offs[lo], local.data(), hi - lo, counts + lo);
+        // every replica is driven by exactly one worker here: its own handle, no per-thread alias needed
+        if (csfm_count_batch(replicas[r].handle(), bytes + offs[lo], local.data(), hi - lo, counts + lo, nullptr) != CSFM_OK)
+          throw_last("count_batch_sharded");
       } catch (...) {
         errors[r] = std::current_exception();
       }
@@ -118,7 +139,7 @@ void FMIndex::count_batch_sharded(const std::vector<FMIndex>& replicas, const ui
 void FMIndex::count_batch(const uint8_t* bytes, const uint64_t* offs, uint64_t npat, uint64_t* counts,
                           uint64_t* sp_ep) const {
   if (!handle_) throw std::runtime_error("count_batch: index not built");
-  if (csfm_count_batch(handle_.get(), bytes, offs, npat, counts, sp_ep) != CSFM_OK) throw_last("count_batch");
+  if (csfm_count_batch(local(), bytes, offs, npat, counts, sp_ep) != CSFM_OK) throw_last("count_batch");
 }
 
 std::vector<uint64_t> FMIndex::count_batch(const std::vector<std::string_view>& patterns) const {
@@ -158,11 +179,12 @@ LocateBatch FMIndex::locate_batch(const std::vector<std::string_view>& patterns,
   uint64_t total = 0;
   uint64_t cap = patterns.size() == 1 ? 0 : std::max<uint64_t>(*locate_hint_, 64 * patterns.size());
   r.positions.resize(cap);
-  int rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
+  csfm_index* const h = local();
+  int rc = csfm_locate_batch(h, bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
                              cap ? r.positions.data() : nullptr, cap, r.status.data(), &total);
   if (rc == CSFM_ERR_CAPACITY || (rc == CSFM_OK && cap == 0 && total != 0)) {
     r.positions.resize(total);
-    rc = csfm_locate_batch(handle_.get(), bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
+    rc = csfm_locate_batch(h, bytes.data(), offs.data(), patterns.size(), limit, r.offsets.data(),
                            r.positions.data(), total, r.status.data(), &total);
   }
   if (rc != CSFM_OK) throw_last("locate_batch");

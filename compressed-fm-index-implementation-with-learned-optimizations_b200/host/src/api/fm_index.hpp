@@ -13,6 +13,7 @@
 #include <memory>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <vector>
 
 struct csfm_index;  // include/csfm.h
@@ -84,6 +85,12 @@ public:
   static void set_default_device(int device);
 
 private:
+  /// The handle a query call of the calling thread goes through: the index's own handle on the thread that created
+  /// it, a thread-local alias over the same device blob (csfm_alias: own streams and workspaces, no copy) on every
+  /// other thread — calls on one C handle are serialised by its mutex, so this is what lets the const query
+  /// methods run concurrently like the reference's (fm_index.hpp: no mutable state).
+  csfm_index* local() const;
+  std::thread::id owner_ = std::this_thread::get_id();
   IndexMeta meta_;
   std::shared_ptr<const std::string> text_;  // host copy for extract(), like FMIndex::text_
   std::shared_ptr<csfm_index> handle_;       // device-resident index; copies share it (read-only)

@@ -188,6 +188,11 @@ CSFM_API int csfm_blob(const csfm_index* idx, const void** d_blob, uint64_t* byt
  * take_ownership == 0 the caller keeps the memory alive for the life of the handle. */
 CSFM_API int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownership,
                               csfm_index** out);
+/* A second handle over the SAME blob on the same device, without a copy: its own streams, workspaces, statistics and
+ * mutex. Calls on ONE handle are serialised by its mutex; host threads that want to query one index concurrently each
+ * take an alias (the C++ class cs::FMIndex does that by itself for every thread other than the one that built the index).
+ * The alias borrows the blob: destroy it before the handle that owns the blob. */
+CSFM_API int csfm_alias(const csfm_index* idx, csfm_index** out);
 /* A second handle over a copy of the blob on `device` (the same device, or a peer: the copy goes over
  * NVLink when peer access can be enabled, else through the host). For single-process callers that want
  * one replica per GPU without a communicator; the new handle owns its copy. */

@@ -65,6 +65,7 @@ def test_cpp_batch_api(tmp_path):
 #include "csfm.h"
 #include <cassert>
 #include <iostream>
+#include <thread>
 int main(int argc, char** argv) {
   (void)argc;
   std::string text;
@@ -110,6 +111,25 @@ int main(int argc, char** argv) {
   assert(lean.count_batch(pats) == counts);
   assert(lean.extract(0, text.size() + 10) == text && lean.extract(4, 5) == text.substr(4, 5));
   assert(lean.extract(text.size() - 3, 100) == text.substr(text.size() - 3) && lean.extract(text.size(), 3).empty());
+  // const query methods from several threads at once (each thread other than the builder gets its own alias handle
+  // over the same device blob: own streams and workspaces, no copy), like the reference's stateless readers
+  {
+    std::vector<std::thread> workers;
+    std::vector<int> ok(6, 0);
+    for (int t = 0; t < 6; ++t)
+      workers.emplace_back([&, t] {
+        bool good = true;
+        for (int rep = 0; rep < 20; ++rep) {
+          good = good && idx.count_batch(pats) == counts;
+          good = good && idx.count(pats[(t + rep) % pats.size()]) == counts[(t + rep) % pats.size()];
+          auto l3 = idx.locate_batch(views, 17);
+          good = good && l3.positions == loc.positions && l3.offsets == loc.offsets;
+        }
+        ok[t] = good;
+      });
+    for (auto& w : workers) w.join();
+    for (int t = 0; t < 6; ++t) assert(ok[t]);
+  }
   // replicas in one process: one per visible GPU (at least two handles, on the same device if there is only one)
   int ndev = 0;
   assert(csfm_device_count(&ndev) == 0 && ndev >= 1);

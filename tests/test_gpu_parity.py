@@ -328,6 +328,45 @@ def test_async_submit_packed_codes(fm, sigma, n):
         idx.count_batch_submit_packed(packed.ctypes.data, d.size + 1, lens.ctypes.data, len(pats), out.ctypes.data)
 
 
+def test_alias_handles_from_threads(fm):
+    """csfm_alias: a second handle over the same blob (no copy) per host thread; every thread gets the oracle's answers
+    while the others are running, and the aliases see the same index as the handle that owns the blob."""
+    import threading
+    rng = np.random.default_rng(3)
+    text, alpha = _rand_text(rng, 200_000, 4, True)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=16))
+    orc = oracle.OracleIndex(text, stride=16)
+    pats = _mixed_patterns(rng, text, alpha, 20_000, 24)
+    d, o = fm.pack_patterns(pats)
+    oc, ose = orc.count_batch(d, o)
+    ooffs, opos, ostatus, _ = orc.locate_batch(d[: int(o[2000])], o[:2001], limit=9)
+    blob_ptr, blob_bytes = idx.blob()
+    errors = []
+
+    def worker(k):
+        try:
+            a = idx.alias()
+            assert a.blob() == (blob_ptr, blob_bytes) and a.info().layout == idx.info().layout
+            for _ in range(5):
+                c, se = a.count_batch(d, o, want_intervals=True)
+                assert (c == oc).all() and (se == ose).all()
+                offs, pos, status = a.locate_batch(d[: int(o[2000])], o[:2001], limit=9)
+                assert (offs == ooffs).all() and (pos == opos).all() and (status == ostatus).all()
+                assert a.count(pats[k]) == int(oc[k])
+            a.close()
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for _ in range(5):
+        assert (idx.count_batch(d, o) == oc).all()     # the owning handle keeps working meanwhile
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_host_offsets_are_checked(fm):
     idx = fm.FMIndex.build_from_text(b"mississippi$", fm.BuildParams(ssa_stride=4))
     d = np.frombuffer(b"ssiissi", np.uint8)
