@@ -1,18 +1,19 @@
-"""GPU, BASELINE.json configs[2] and configs[3] at FULL size, through properties that do not need a CPU
-index of that size (the oracle's restatement at n = 2^30 would take minutes and tens of GB):
+"""GPU, BASELINE.json configs[2] and configs[3] at FULL size. No CPU index of that size exists (the oracle's
+restatement at n = 2^30 would take minutes and tens of GB), so the expected values come from an INDEPENDENT checker,
+tests/sa_checker.py: the GPU-built suffix array is certified by the O(n) checker (a certified SA is THE reference SA:
+suffixes are distinct and sais.hpp:13's order is total), and for a text with a unique smallest terminator the reference's
+interval of a pattern is [lower_bound, upper_bound) among the suffixes and locate reports SA[sp], SA[sp+1], ... — both
+bounds by binary search with direct text comparisons in plain torch; nothing of the engine's index takes part.
 
   C3  n = 2^30 bytes, sigma = 256, 1 M text-sampled patterns of length 8..32 (the bench workload)
-      * the GPU-built suffix array passes the O(n) certificate (a certified SA is THE reference SA:
-        suffixes are distinct and sais.hpp:13's order is total), BWT and SSA equal their definitions
-        over it (bwt.hpp:10-13, fm_index.cpp:57-65);
-      * the default count kernel (text verification) == the stepping kernel (every character a rank
-        step) on all 1 M patterns, and both report at least one occurrence of every sampled pattern;
-      * count(p) == a naive scan of the text for a sample of patterns (the text ends in a unique
-        smallest byte, so the BWT's cyclic wrap-around cannot add matches);
-      * locate(p) positions, sorted == the naive scan's positions; every position starts an occurrence.
-  C4  n = 2^28 DNA + '$', ssa_stride 32, text-sampled patterns of length 10 (~257 occurrences each)
-      * the same naive-scan checks for count and locate;
-      * sum of the counts == number of located positions (limit above every count);
+      * SA certificate; BWT, SSA and C equal their definitions over it (bwt.hpp:10-13, fm_index.cpp:36-65);
+      * all 10^6 counts of the default kernel (tables + text verification) and of the stepping kernel, and all 10^6
+        intervals, equal the checker's; a second batch with misses, 1..3-byte patterns and a 200-byte pattern too;
+      * located positions equal SA[sp .. sp + min(count, limit)) IN ORDER (limit 100000 and 2);
+      * (kept from round 1) default kernel == stepping kernel, counts and sorted positions == a naive scan of the text.
+  C4  n = 2^28 DNA + '$', ssa_stride 32, the config's 1 M text-sampled patterns of length 10 (~257 occurrences each)
+      * SA certificate; all counts and intervals == the checker's; all 2.6e8 located positions IN ORDER;
+      * the length-12 set with limit 7; `limit` keeps the FIRST rows; naive-scan spot checks;
       * the LF-walking index and the index with a resident suffix array report identical positions.
 """
 import pytest
