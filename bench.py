@@ -164,6 +164,26 @@ L2_RESIDENT_BYTES = 126 << 20   # an index up to the L2 size is served mostly fr
 RANDOM_FETCH_CEILING = 37.3e9    # random 128-byte line fetches/s out of HBM (profiles/r1_gather_probe.json, 4 GiB buffer)
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank's host thread (and so its pinned allocations, first touch) on the CPUs NVML reports as
+    local to its GPU. A no-op on boxes whose GPUs all hang off one NUMA node (the B200 boxes of this pool)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu}
+        allowed = os.sched_getaffinity(0)
+        use = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, use)
+        return {"cpus": len(use), "of": len(allowed), "source": "nvmlDeviceGetCpuAffinity", "restricted": len(use) < len(allowed)}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": repr(e)}
+
+
 def kernel_sources_sha16():
     """Identifies the kernel sources a committed ncu capture belongs to (.git does not travel to the GPU box)."""
     import hashlib
@@ -1261,6 +1281,7 @@ def run_engine(args, rank, world, local_rank):
     import csfm_b200 as fm
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    affinity = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: first touch decides the node
     t_start = time.perf_counter()
     line = count_leg(args, args.workload, rank, world, local_rank, args.steps, args.warmup, full=True)
     legs_s = {"main": time.perf_counter() - t_start}
@@ -1306,6 +1327,7 @@ def run_engine(args, rank, world, local_rank):
         configs.update({"c2": c2, "c4": "see `locate`", "c5": c5})
     if rank != 0:
         return
+    line["config"]["host_affinity"] = affinity
     line["locate"] = locate
     if configs:
         line["configs"] = configs
