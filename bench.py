@@ -164,6 +164,29 @@ L2_RESIDENT_BYTES = 126 << 20   # an index up to the L2 size is served mostly fr
 RANDOM_FETCH_CEILING = 37.3e9    # random 128-byte line fetches/s out of HBM (profiles/r1_gather_probe.json, 4 GiB buffer)
 
 
+_ALL_CPUS = None
+
+
+class all_host_cpus:
+    """The CPU baselines use every host core: lift the NUMA-local restriction of this rank while they run."""
+
+    def __enter__(self):
+        self.saved = None
+        try:
+            if _ALL_CPUS:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, _ALL_CPUS)
+        except Exception:
+            self.saved = None
+
+    def __exit__(self, *exc):
+        try:
+            if self.saved:
+                os.sched_setaffinity(0, self.saved)
+        except Exception:
+            pass
+
+
 def pin_to_gpu_numa_node(local_rank):
     """Best effort: run this rank's host thread (and so its pinned allocations, first touch) on the CPUs NVML reports as
     local to its GPU. A no-op on boxes whose GPUs all hang off one NUMA node (the B200 boxes of this pool)."""
@@ -176,7 +199,9 @@ def pin_to_gpu_numa_node(local_rank):
         ncpu = os.cpu_count() or 1
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu}
+        global _ALL_CPUS
         allowed = os.sched_getaffinity(0)
+        _ALL_CPUS = set(allowed)
         use = (cpus & allowed) or allowed
         os.sched_setaffinity(0, use)
         return {"cpus": len(use), "of": len(allowed), "source": "nvmlDeviceGetCpuAffinity", "restricted": len(use) < len(allowed)}
@@ -580,7 +605,8 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
 
     if cpu_budget > 0:
         try:
-            out["cpu_baseline"] = locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, cpu_budget)
+            with all_host_cpus():
+                out["cpu_baseline"] = locate_cpu_baseline(fm, idx, text, bytes_d, offs_d, plen, cpu_budget)
         except Exception as e:  # pragma: no cover
             out["cpu_baseline"] = {"value": None, "unit": "occurrences/s", "kind": "reference", "sample": f"unavailable: {e!r}"}
     idx.close()
@@ -1060,7 +1086,8 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
             t_inject = time.perf_counter() - t0
             hb, ho = h_batches[0]
             data, offs = hb.numpy(), ho.numpy().astype(np.uint64)
-            out, q, dt = reference_timed_sample(ref, data, offs, args.cpu_budget if full else min(args.cpu_budget, 8.0), nthreads)
+            with all_host_cpus():
+                out, q, dt = reference_timed_sample(ref, data, offs, args.cpu_budget if full else min(args.cpu_budget, 8.0), nthreads)
             ok = bool((out[:q] == c0[:q].astype(np.uint64)).all())
             cpu = {"value": q / dt, "unit": "queries/s", "cores": nthreads, "kind": "reference",
                    "sample": f"first {q} queries of batch 0 in {dt:.1f} s on {nthreads} std::threads (reference index injected in {t_inject:.0f} s)",
