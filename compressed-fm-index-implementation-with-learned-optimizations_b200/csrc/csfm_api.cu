@@ -46,6 +46,11 @@ void DeviceBuffer::release() {
 
 DeviceGuard::DeviceGuard(int dev) {
   if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+  if (prev == dev) {  // the common case: nothing to switch, nothing to restore (two driver calls less per query)
+    prev = -1;
+    ok = true;
+    return;
+  }
   ok = (cudaSetDevice(dev) == cudaSuccess);
 }
 DeviceGuard::~DeviceGuard() {
@@ -560,8 +565,14 @@ bool single_path_ok(const csfm_index* idx, uint64_t len) {
 
 int count_single(csfm_index* idx, const uint8_t* bytes, uint32_t len, uint64_t* count, uint64_t* sp, uint64_t* ep) {
   SingleQuery q;
-  if (len) std::memcpy(q.bytes, bytes, len);
+  const BlobHeader& h = idx->h;
+  for (uint32_t i = 0; i < len; ++i) {  // argument marshalling: the per-character table entries ride in the parameters
+    const uint32_t b = bytes[i], code = h.code_of_byte[b];
+    q.ent[i] = make_uint4(h.base_by_byte[b], code | (h.C[b + 1] == h.C[b] ? 0x80000000u : 0u), h.start1[(code >> 4) & 15u], h.C[b]);
+  }
   q.len = len;
+  q.c_after_last = len ? h.C[(uint32_t)bytes[len - 1] + 1] : 0u;
+  q.pad = 0;
   q.seq = ++idx->single_seq;
   if (q.seq == 0) q.seq = ++idx->single_seq;  // 0 is the value of a fresh result slot
   auto* d_res = reinterpret_cast<SingleResult*>(static_cast<uint8_t*>(idx->d_pinned) + kSingleResultAt);
@@ -576,6 +587,7 @@ int count_single(csfm_index* idx, const uint8_t* bytes, uint32_t len, uint64_t* 
     }
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  // result and sequence number were written by ONE 16-byte store (one cache line, one transaction)
   *count = res->count;
   if (sp) *sp = res->sp;
   if (ep) *ep = res->ep;

@@ -281,15 +281,18 @@ struct CountArgs {
 // Single-query path (cs::FMIndex::count / locate called one pattern at a time, tools/benchmark.cpp): the
 // pattern travels as a kernel PARAMETER and the result comes back through mapped pinned memory that
 // the host spins on, so a query is one launch: no staging copies, no stream synchronisation.
-constexpr uint32_t kSingleMax = 240;
+constexpr uint32_t kSingleMax = 64;  // longer single patterns go through the batch path
 struct SingleQuery {
-  uint8_t bytes[kSingleMax];
+  // what a step needs to know about each pattern character, looked up ON THE HOST from its copy of the header tables
+  // and handed over as kernel parameters (constant bank): x = base, y = compact code | absent << 31, z = start1[hi], w = C[byte]
+  uint4 ent[kSingleMax];
   uint32_t len;
-  uint32_t seq;  // written to SingleResult::seq last: the host waits for it
+  uint32_t c_after_last;  // C[last byte + 1]: the end of the interval of a pattern that starts from the C array
+  uint32_t seq;           // stored with the result: the host waits for it
+  uint32_t pad;
 };
-struct SingleResult {
-  unsigned long long count, sp, ep;
-  unsigned int seq, pad;
+struct alignas(16) SingleResult {  // ONE 16-byte store: count, interval and the sequence number land together
+  unsigned int count, sp, ep, seq;   // (counts and rows are < 2^32: n < 2^32 - 1)
 };
 
 struct WalkArgs {

@@ -913,27 +913,19 @@ count2_tma_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// count for ONE pattern: one warp, the pattern in the kernel parameters, the result (count and interval)
-// written to mapped pinned host memory followed by the sequence number the host is spinning on.
+// count for ONE pattern: one warp, the pattern (as per-character step entries) in the kernel parameters, the result
+// (count, interval, sequence number) written to mapped pinned host memory in one 16-byte store the host is spinning on.
 // Same search as count2_kernel<false,.>: k-mer table for the last k characters, then one rank step per
 // character (fm_index.cpp:79-101).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ SingleQuery sq, SingleResult* __restrict__ res) {
-  __shared__ uint4 ent[kSingleMax];  // per pattern character: x = base, y = code | absent << 31, z = start1[hi], w = C[byte]
   const int lane = threadIdx.x;
   const int j = lane & 3;
-  const BlobHeader* __restrict__ h = iv.hdr;
   const uint32_t m = sq.len;
   const bool two = iv.L == 2;
-  // every table entry the query will need, fetched at once: two dependent rounds of L2 hits instead of two per step
-  for (uint32_t i = lane; i < m; i += 32) {
-    const uint32_t b = sq.bytes[i];
-    const uint32_t c0 = h->C[b], c1 = h->C[b + 1];
-    const uint32_t code = h->code_of_byte[b];
-    ent[i] = make_uint4(h->base_by_byte[b], code | (c1 == c0 ? 0x80000000u : 0u), h->start1[code >> 4], c0);
-  }
-  __syncwarp();
+  const uint4* const ent = sq.ent;  // per pattern character, in the kernel parameters: no table fetch before the first rank
+  const uint32_t c_after_last = sq.c_after_last;
   uint32_t sp = 0, ep = 0;
   unsigned long long cnt = 0;
   if (m == 0) {
@@ -965,7 +957,7 @@ count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant
     } else {
       const uint4 x = ent[m - 1];
       sp = x.w;  // first step needs no rank: [C[c], C[c+1])
-      ep = h->C[(uint32_t)sq.bytes[m - 1] + 1];
+      ep = c_after_last;
       i = (int)m - 2;
     }
     alive = alive && sp < ep;
@@ -990,11 +982,9 @@ count_single2_kernel(const __grid_constant__ IndexView iv, const __grid_constant
     else sp = ep = 0;
   }
   if (lane == 0) {
-    res->count = cnt;
-    res->sp = sp;
-    res->ep = ep;
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned int*>(&res->seq) = sq.seq;
+    // one 16-byte store to the mapped pinned slot: a single write transaction on the link, so the host that sees the
+    // new sequence number sees the result with it (no system-scope fence between result and flag)
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(res), "r"((uint32_t)cnt), "r"(sp), "r"(ep), "r"(sq.seq) : "memory");
   }
 }
 
