@@ -1021,7 +1021,13 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "frac_basis": basis,
                     "line_fetches_per_s": fetches / t_launch_s,
                     "random_fetch_ceiling_lines_per_s": fetch_ceiling,
-                    "frac_of_random_fetch_ceiling": fetches / t_launch_s / fetch_ceiling}
+                    "frac_of_random_fetch_ceiling": fetches / t_launch_s / fetch_ceiling,
+                    "frac_of_random_fetch_ceiling_note": "index fetches the launch executed (level lines + table entries + suffix-array "
+                                                         "entries + text windows) per second over the probe's ceiling for this line size"}
+        if traffic and line_bytes == 128:
+            # the same by DRAM traffic: every 128 bytes moved counted as one line (includes the streamed batch and results)
+            roofline["dram_lines_per_s"] = traffic / 128 / t_launch_s
+            roofline["frac_of_random_fetch_ceiling_by_dram_traffic"] = traffic / 128 / t_launch_s / fetch_ceiling
     roofline.update({
         "traffic_capture": traffic_meta,
         "model": {"bytes_per_launch": model_bytes, "gbs": model_bytes / t_launch_s / 1e9, "frac_of_hbm_peak": model_bytes / t_launch_s / 1e9 / peak,
