@@ -524,8 +524,10 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
     // layout 3: keys are built from the two-bit codes only (a pattern that contains the symbol occurring once
     // starts from the C array instead), so the table has 4^k entries, not 5^k
     const uint64_t radix = (flags & CSFM_BUILD_NO_COMPACT) ? 256 : dna ? std::min<uint64_t>(h.sigma, 4) : h.sigma;
-    // a quarter of a byte per text symbol (layout 2 on bytes <= 16 symbols: a quarter of the level bytes)
-    uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, dna ? n / 4 : (uint64_t)L * h.level_stride / 4));
+    // layout 2: a quarter of the level bytes. Layout 3: half a byte per text symbol (1.5 x its level bytes) — its
+    // count kernel is bound by issue slots, every character the lookup covers is a tenth of a 20-mer's work:
+    // measured on C2 k = 10 / 11 / 12 -> 7.4 / 8.1 / 8.7e9 q/s at 39 / 64 / 165 MB; k = 11 keeps the index at the size of the text
+    uint64_t budget = std::min<uint64_t>(1024ull << 20, std::max<uint64_t>(1ull << 20, dna ? n / 2 : (uint64_t)L * h.level_stride / 4));
     if (flags & CSFM_BUILD_LARGE_TABLE) {
       // opt-in: spend device memory on the table so that the lookup itself leaves few rows and the
       // query goes straight to the text verification (k = 4 for a byte alphabet at n = 2^30: 34 GB;
