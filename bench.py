@@ -505,8 +505,10 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
         tmeta["scaled_to_occurrences"] = total_all / world
     elif traffic:
         traffic, tmeta = None, {"valid": False, "why": "capture does not say how many occurrences it walked"}
-    in_l2 = int(info.blob_bytes) <= L2_RESIDENT_BYTES
-    ws_peak, ws_src = l2_random_peak(int(info.blob_bytes), lb)
+    # what the walk touches: the level lines and the samples (the k-mer table is only read by the count pass)
+    walk_set = int(info.blocks_per_level) * lb * L + int(info.nsamp) * 4
+    in_l2 = walk_set <= L2_RESIDENT_BYTES and int(info.blob_bytes) <= L2_RESIDENT_BYTES
+    ws_peak, ws_src = l2_random_peak(walk_set, lb)
     achieved_exec = alg / world / t_s / 1e9
     if in_l2:
         roof = {"bound": "l2", "achieved": achieved_exec, "peak": ws_peak, "frac": achieved_exec / ws_peak, "peak_source": ws_src,
@@ -524,7 +526,8 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
     out = {"metric": "locate occurrences/sec", "value": total_all / t_s, "unit": "occurrences/s", "n_gpus": world,
            "ms_per_batch": ms, "scaling": "weak",
            "config": {"workload": f"C4: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen} per GPU, limit {limit}",
-                      "levels": L, "line_bytes": lb, "layout": int(info.layout), "index_bytes": int(info.blob_bytes), "index_build_s": build_s,
+                      "levels": L, "line_bytes": lb, "layout": int(info.layout), "index_bytes": int(info.blob_bytes),
+                      "walk_working_set_bytes": walk_set, "kmer_k": int(info.kmer_k), "index_build_s": build_s,
                       "index_broadcast_ms": bcast_ms},
            "occurrences_per_batch": int(total_all), "lf_steps_per_occurrence": lf_all / max(1, total_all),
            "roofline": roof,
