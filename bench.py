@@ -652,6 +652,8 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
     t_text = time.perf_counter() - t0
     build_s = bcast_ms = None
     if rank == 0:
+        torch.cuda.empty_cache()  # the builder allocates with cudaMalloc: give it what torch's cache is holding
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         idx = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=wl["stride"]), device=local_rank,
                                                 flags=(fm.BUILD_LAYOUT_BINARY64 if args.layout == 1 else 0) |

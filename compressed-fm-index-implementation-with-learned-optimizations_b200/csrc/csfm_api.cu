@@ -4,7 +4,9 @@
 // workspace reuse, accounting. No algorithm lives here and nothing here can run a query on the
 // CPU: every path ends in a kernel launch from csfm_query.cu / csfm_build.cu / csfm_sa.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -21,6 +23,25 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
+}
+
+static double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+PhaseTimer::PhaseTimer(const char* w) : on(std::getenv("CSFM_BUILD_TIMERS") != nullptr), t0(0), what(w) {
+  if (on) {
+    cudaDeviceSynchronize();
+    t0 = now_s();
+  }
+}
+void PhaseTimer::mark(const char* phase) {
+  if (!on) return;
+  cudaDeviceSynchronize();
+  const double t = now_s();
+  std::fprintf(stderr, "[csfm build] %s / %s: %.1f ms\n", what, phase, 1e3 * (t - t0));
+  t0 = t;
 }
 
 int DeviceBuffer::ensure(size_t bytes) {

@@ -456,6 +456,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   if (n > kMaxN) return fail(CSFM_ERR_TOO_LARGE, "text length must be < 2^32 - 1");
   if (stride == 0) return fail(CSFM_ERR_INVALID, "ssa_stride must be > 0");
   cudaStream_t st = nullptr;  // construction runs on the legacy default stream of the device
+  PhaseTimer pt("index");
 
   // 1) byte histogram -> C, compact codes, level count, per-symbol base
   unsigned long long* d_hist = nullptr;
@@ -585,6 +586,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
     return fail(CSFM_ERR_NOMEM, std::string("cudaMalloc(index blob): ") + cudaGetErrorString(e));
   }
 
+  pt.mark("histogram, tables, blob allocation");
   // 2) levels
   uint8_t *d_cur = nullptr, *d_nxt = nullptr;
   uint32_t *d_pop = nullptr, *d_rank = nullptr;
@@ -672,6 +674,7 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
       }
     }
   }
+  pt.mark("levels");
   // 3) SA samples (+ text and suffix array for the verification shortcut) + header
   if (nsamp)
     BUILD_CUDA(cudaMemcpyAsync(idx->d_blob + h.off_ssa, d_ssa, nsamp * 4, cudaMemcpyDeviceToDevice, st));
@@ -689,8 +692,10 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   BUILD_CUDA(cudaGetLastError());
   cleanup();
 #undef BUILD_CUDA
+  pt.mark("samples, text sections, header");
   int rc = index_finish_handle(idx);
   if (rc == CSFM_OK && h.kmer_k) rc = dna ? build_kmer_table3(idx, st) : build_kmer_table(idx, st);  // backward search over the finished levels
+  pt.mark("handle + k-mer / half-step tables");
   if (rc != CSFM_OK) {
     csfm_destroy(idx);
     return rc;

@@ -24,6 +24,15 @@ int fail(int code, const std::string& msg);
     }                                                                                       \
   } while (0)
 
+// CSFM_BUILD_TIMERS=1: wall-clock of the construction phases on stderr (each mark synchronises the device).
+struct PhaseTimer {
+  bool on;
+  double t0;
+  const char* what;
+  explicit PhaseTimer(const char* w);
+  void mark(const char* phase);
+};
+
 // Grow-only device buffer (workspace reuse across batch calls).
 struct DeviceBuffer {
   void* p = nullptr;

@@ -210,6 +210,7 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
     }                                                                                        \
   } while (0)
 
+  PhaseTimer pt("suffix array");
   // 8-byte slack on the key buffers: the sparse rounds carve them into halves
   SA_CUDA(cudaMalloc(&key_a, n * 8 + 64));
   SA_CUDA(cudaMalloc(&key_b, n * 8 + 64));
@@ -220,6 +221,7 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
   SA_CUDA(cudaMalloc(&d_present, 256 * 4));
   SA_CUDA(cudaMalloc(&d_ngroups, 16));
 
+  pt.mark("allocate 32 n bytes");
   int dev = 0, num_sms = 148;
   SA_CUDA(cudaGetDevice(&dev));
   SA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -251,6 +253,7 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
   const size_t tmp_bytes = std::max(std::max(tmp_sort, tmp_scan), tmp_scan8) + 256;
   SA_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
 
+  pt.mark("alphabet + packed keys");
   int nbits_n = 1;
   while ((1ull << nbits_n) < n + 1) ++nbits_n;
   uint64_t h = (uint64_t)k0;
@@ -298,6 +301,7 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
       return fail(CSFM_ERR_CUDA, "suffix sorting did not converge");
     }
   }
+  pt.mark("dense rounds (sort all n pairs, group heads, ranks, unresolved rows)");
   uint32_t* const sa_final = vals.Current();
   if (sparse) {
     // ---- sparse rounds (u <= n / 2): all buffers are carved out of the dense ones -------------------------
@@ -339,6 +343,7 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
       }
     }
   }
+  pt.mark("sparse rounds");
   if (rounds_out) *rounds_out = rounds;
   if (passes_out) *passes_out = passes;
   if (pair_passes_out) *pair_passes_out = pair_passes;
@@ -351,7 +356,9 @@ int build_sa_bwt_device(const uint8_t* d_text, uint64_t n, uint32_t stride, cuda
   if (d_sa_out) {  // hand the SA buffer over instead of freeing it
     if (d_sa == sa_a) { *d_sa_out = sa_a; sa_a = nullptr; } else { *d_sa_out = sa_b; sa_b = nullptr; }
   }
+  pt.mark("BWT + samples");
   cleanup();
+  pt.mark("free");
 #undef SA_CUDA
   *d_bwt_out = d_bwt;
   *d_ssa_out = d_ssa;
