@@ -106,7 +106,7 @@ using namespace csfm;
 extern "C" {
 
 const char* csfm_last_error(void) { return g_last_error.c_str(); }
-const char* csfm_version(void) { return "csfm-b200 0.1 (sm_100a)"; }
+const char* csfm_version(void) { return "csfm-b200 0.2 (sm_100a)"; }
 
 int csfm_device_count(int* count) {
   if (!count) return fail(CSFM_ERR_INVALID, "count is null");
