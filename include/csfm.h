@@ -22,6 +22,11 @@
  *    quirks: count("") == n, cyclic over-count without a terminator, locate
  *    positions in SA-row order, an error status where the reference throws;
  *  - n must be < 2^32 - 1, as in the reference (uint32 SA / C array, fm_index.hpp:43-44);
+ *  - threads: every call on a handle is serialised by that handle's mutex (safe, not concurrent); host threads that
+ *    want to query one index concurrently take an alias each (csfm_alias: a second handle over the same device blob,
+ *    own streams and workspaces, no copy);
+ *  - a single pattern (npat == 1, up to 64 bytes, layout 2) takes a one-launch path: the pattern rides in the kernel
+ *    parameters and the result comes back through mapped pinned memory, about 10 us per call;
  *  - there is no CPU fallback: without a usable CUDA device every call fails with
  *    CSFM_ERR_CUDA.
  */

@@ -367,6 +367,41 @@ def test_alias_handles_from_threads(fm):
     assert not errors, errors
 
 
+def test_new_entry_points_edge_cases(fm):
+    """Argument edges of the round-2 entry points: extract at and beyond the end, empty packed batches, aliases that
+    outlive nothing, single-pattern calls at the 64-byte boundary of the one-launch path."""
+    text = np.concatenate([np.frombuffer(b"abracadabra" * 40, np.uint8), np.zeros(1, np.uint8)])
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=4))
+    orc = oracle.OracleIndex(text, stride=4)
+    lean = fm.FMIndex.from_host_blob(idx.blob_to_host())
+    raw = text.tobytes()
+    assert lean.extract(len(raw) - 1, 1) == raw[-1:] and lean.extract(len(raw), 1) == b"" and lean.extract(0, 0) == b""
+    assert lean.extract(3, 10**12) == raw[3:]
+    # empty packed batch, batch of empty patterns
+    out = np.zeros(4, np.uint32)
+    lens0 = np.zeros(3, np.uint8)
+    one = np.zeros(1, np.uint8)
+    idx.count_batch_wait(idx.count_batch_submit_packed(one.ctypes.data, 0, lens0.ctypes.data, 0, out.ctypes.data))
+    idx.count_batch_wait(idx.count_batch_submit_packed(one.ctypes.data, 0, lens0.ctypes.data, 3, out.ctypes.data))
+    assert out[:3].tolist() == [len(raw)] * 3                       # count("") == n (fm_index.cpp:80)
+    # single-pattern calls around the parameter-space limit (64 bytes) agree with the batch kernels and the oracle
+    for m in (1, 2, 63, 64, 65, 200):
+        pat = raw[5:5 + m]
+        want = orc.count(pat)
+        assert idx.count(pat) == want
+        d, o = fm.pack_patterns([pat, pat])
+        assert idx.count_batch(d, o).tolist() == [want, want]
+        assert idx.locate(pat, 7) == orc.locate(pat, 7)[0]
+    # an alias closed before its owner, and a second one taken afterwards
+    a = idx.alias()
+    assert a.count(b"abra") == orc.count(b"abra")
+    a.close()
+    b = idx.alias()
+    assert b.locate(b"cad", 3) == orc.locate(b"cad", 3)[0]
+    b.close()
+    assert idx.count(b"abra") == orc.count(b"abra")
+
+
 def test_host_offsets_are_checked(fm):
     idx = fm.FMIndex.build_from_text(b"mississippi$", fm.BuildParams(ssa_stride=4))
     d = np.frombuffer(b"ssiissi", np.uint8)
