@@ -1,4 +1,6 @@
-# A/B runs of the C3 default count kernel: CTAs per SM (experiment build) and the refill knobs (environment)
+# A/B runs of the C3 default count kernel: CTAs per SM (experiment build:
+#   CSFM_OUT=$PK/libcsfm_v7.so CSFM_NVCC_EXTRA="-DCSFM_SHORTCUT_CTAS=7" bash $PK/build.sh -f) and the refill knobs (environment).
+# Result on one B200 (profiles/README.md §R2.3): default 6.42e9, 7 CTAs 5.35e9, knobs within 1 %.
 mkdir -p gpurun_out
 PK=compressed-fm-index-implementation-with-learned-optimizations_b200
 B="python bench.py --steps 100 --no-cpu-baseline --no-configs --no-locate --no-large-table"
