@@ -70,11 +70,19 @@ def log(*a):
 # Exactly ONE line may reach stdout (the JSON line). Libraries write banners to fd 1 (NCCL prints
 # its version there), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
 # private duplicate of the original stdout.
-_REAL_STDOUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Called once by main(): from here on everything written to fd 1 goes to stderr, except emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line: dict):
+    claim_stdout()
     _REAL_STDOUT.write(json.dumps(line) + "\n")
     _REAL_STDOUT.flush()
 
@@ -1392,6 +1400,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE.json configs (c1, c2, c5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,54 @@
+"""CPU: the bookkeeping of bench.py that decides which evidence a bench line may carry: a committed ncu capture is
+used only when it was taken from the kernel sources in this tree AND names the kernel the run launches (a stale file must
+not decorate a new kernel), and the L2 / working-set ceilings come from the committed probe."""
+import json
+import os
+
+import pytest
+
+import bench
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_committed_capture_matches_these_sources():
+    doc = json.load(open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json")))
+    if doc["source_sha16"] != bench.kernel_sources_sha16():
+        pytest.skip("csrc/ changed since the captures were taken: bench.py reports traffic = null until "
+                    "tools/profile_round.sh + tools/profile_collect.sh are re-run on a B200")
+    for key, kernel in (("c3", "count2_kernel<true,false>"), ("c3_stepping", "count2_kernel<false,false>"), ("c2", "count3_kernel"),
+                        ("c5", "count3_kernel"), ("c4_walk", "walk3_kernel")):
+        bytes_, meta = bench.committed_traffic(key, kernel)
+        assert meta["valid"] and bytes_ > 0, (key, meta)
+
+
+def test_stale_or_foreign_captures_are_dropped(tmp_path, monkeypatch):
+    doc = json.load(open(os.path.join(ROOT, "profiles", "count_kernel_traffic.json")))
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "kernel_sources_sha16", lambda: doc["source_sha16"])
+    (prof / "count_kernel_traffic.json").write_text(json.dumps(doc))
+    assert bench.committed_traffic("c3", "count2_kernel<true,false>")[0] > 0
+    # a capture of another kernel under the same key
+    assert bench.committed_traffic("c3", "count3_kernel")[0] is None
+    # a key that was never captured
+    got, meta = bench.committed_traffic("c9", "count2_kernel")
+    assert got is None and not meta["valid"]
+    # the sources moved on: every capture is stale
+    stale = dict(doc, source_sha16="0" * 16)
+    (prof / "count_kernel_traffic.json").write_text(json.dumps(stale))
+    got, meta = bench.committed_traffic("c3", "count2_kernel<true,false>")
+    assert got is None and "belongs to sources" in meta["why"]
+    # no file at all
+    os.remove(prof / "count_kernel_traffic.json")
+    assert bench.committed_traffic("c3", "count2_kernel<true,false>")[0] is None
+
+
+def test_working_set_ceilings_come_from_the_probe():
+    small, src = bench.l2_random_peak(30 << 20, 64)
+    big, _ = bench.l2_random_peak(1 << 30, 64)
+    mid, _ = bench.l2_random_peak(123 << 20, 64)
+    assert "r2_l2_sweep_probe.json" in src
+    assert small > mid > big > 0          # the fetch rate falls as the working set outgrows the L2
+    assert bench.l2_random_peak(30 << 20, 128)[0] > bench.l2_random_peak(300 << 20, 128)[0]
