@@ -479,6 +479,8 @@ int csfm_alias(const csfm_index* idx, csfm_index** out) {
     (*out)->tma_staging = idx->tma_staging;
     (*out)->no_two_pass = idx->no_two_pass;
     (*out)->no_sa_locate = idx->no_sa_locate;
+    (*out)->count3_lanes = idx->count3_lanes;
+    (*out)->walk3_lanes = idx->walk3_lanes;
     (*out)->view = idx->view;  // the same experiment knobs as the handle it aliases
   }
   return rc;

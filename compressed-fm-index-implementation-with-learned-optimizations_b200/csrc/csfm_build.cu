@@ -422,6 +422,8 @@ int index_finish_handle(csfm_index* idx) {
   v.verify_min = h.verify_min ? h.verify_min : (h.levels >= 2 ? 3u : 8u);
   if (const char* e = std::getenv("CSFM_VERIFY_MIN")) v.verify_min = (uint32_t)std::atoi(e);
   idx->no_sa_locate = std::getenv("CSFM_NO_SA_LOCATE") != nullptr;
+  if (const char* e = std::getenv("CSFM_COUNT3_LANES")) idx->count3_lanes = std::atoi(e) == 1 ? 1 : 2;
+  if (const char* e = std::getenv("CSFM_WALK3_LANES")) idx->walk3_lanes = std::atoi(e) == 1 ? 1 : 2;
   // measured slower than the one-pass sub-warp kernel (profiles/README.md): selectable for A/B runs only
   idx->no_two_pass = std::getenv("CSFM_TWO_PASS") == nullptr;
   v.refill_min = 8;

@@ -180,6 +180,55 @@ __device__ __forceinline__ Chunk32 ldg_nc_v8(const void* p) {
   return r;
 }
 
+// L2 residency hints for the layout-3 kernels (CSFM_L2_HINTS: 0 none, 1 one-shot data evict-first, 2 + index lines and
+// table entries evict-last): what a walk or a search comes back to (level lines, k-mer table) should outlive what it
+// touches once (suffix-array samples, result stores) in a 126 MB L2 that the index only just fits or just exceeds.
+#ifndef CSFM_L2_HINTS
+#define CSFM_L2_HINTS 0
+#endif
+__device__ __forceinline__ Chunk32 ldg_line_keep(const void* p) {
+#if CSFM_L2_HINTS >= 2
+  Chunk32 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.c0), "=r"(r.c1), "=r"(r.c2), "=r"(r.c3), "=r"(r.p0), "=r"(r.p1), "=r"(r.p2), "=r"(r.p3)
+               : "l"(p));
+  return r;
+#else
+  return ldg_nc_v8(p);
+#endif
+}
+__device__ __forceinline__ uint2 ldg_table_keep(const uint2* p) {
+#if CSFM_L2_HINTS >= 2
+  uint64_t pol;
+  uint2 r;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ uint32_t ldg_once_u32(const uint32_t* p) {
+#if CSFM_L2_HINTS >= 1
+  uint64_t pol;
+  uint32_t r;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ void stg_once_u64(uint64_t* p, uint64_t v) {
+#if CSFM_L2_HINTS >= 1
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+#else
+  *p = v;
+#endif
+}
+
 // A Chunk32 whose registers are "defined" for the compiler without costing an instruction. Lanes
 // that skip the load (inactive sub-warp, or ep in the same line as sp) compute on garbage that is
 // discarded: results only travel inside the 4-lane group and are committed under `if (active)`.

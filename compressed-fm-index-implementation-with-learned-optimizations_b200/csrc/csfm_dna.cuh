@@ -77,6 +77,26 @@ __device__ __forceinline__ uint32_t dna_symbol(const Chunk32& k, uint32_t off, i
 }
 __device__ __forceinline__ uint32_t group2_sum(uint32_t v) { return v + __shfl_xor_sync(0xFFFFFFFFu, v, 1); }
 
+// ---- one LANE per line (L2-resident indexes: count3_kernel<., 1>): the lane holds both halves A and B of the line ----
+// the six hit words of the whole line for value v, and the counter of v
+__device__ __forceinline__ void dna_line_hits(const Chunk32& A, const Chunk32& B, uint32_t v, uint32_t (&x)[6], uint32_t& cnt) {
+  const uint32_t m0 = bit_fill(v, 0), m1 = bit_fill(v, 1);
+  x[0] = ~((A.c2 ^ m0) | (A.c3 ^ m1));
+  x[1] = ~((A.p0 ^ m0) | (A.p1 ^ m1));
+  x[2] = ~((A.p2 ^ m0) | (A.p3 ^ m1));
+  x[3] = ~((B.c2 ^ m0) | (B.c3 ^ m1));
+  x[4] = ~((B.p0 ^ m0) | (B.p1 ^ m1));
+  x[5] = ~((B.p2 ^ m0) | (B.p3 ^ m1));
+  cnt = pick4(A.c0, A.c1, B.c0, B.c1, v);
+}
+// counter + hits below the in-line offset off (0..191)
+__device__ __forceinline__ uint32_t dna_line_rank(uint32_t cnt, const uint32_t (&x)[6], uint32_t off) {
+  uint32_t r = cnt;
+#pragma unroll
+  for (int t = 0; t < 6; ++t) r += (uint32_t)__popc(x[t] & low_mask((int)off - 32 * t));
+  return r;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace csfm

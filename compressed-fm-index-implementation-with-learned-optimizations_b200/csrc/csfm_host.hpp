@@ -98,6 +98,8 @@ struct csfm_index {
   } qslot[8];
   uint32_t qslot_next = 0;
   uint32_t two_pass_skip = 0;   // calls for which the two-pass form is skipped (most queries of recent batches overflowed)
+  int count3_lanes = 0;         // CSFM_COUNT3_LANES=1|2: lanes per query of the layout-3 count kernel (0: by index size)
+  int walk3_lanes = 0;          // CSFM_WALK3_LANES=1|2: lanes per row of the layout-3 walk kernel (0: by index size)
   bool no_two_pass = true;      // the two-pass form is opt-in (CSFM_TWO_PASS=1): measured slower than the one-pass sub-warp kernel
 
   uint8_t* d_text_cache = nullptr;  // csfm_extract on an index without a text section: the text, rebuilt once by LF walks

@@ -344,9 +344,14 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   const bool nib = idx->view.layout == kLayoutNibble128;
   const bool dna = idx->view.layout == kLayoutDna64;
   const bool tma = idx->tma_staging;
-  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_count3(a)
+  // layout 3: one lane per query while what the search touches (level lines + k-mer table) lives in the L2 — measured on
+  // C2 (56 MB): 1.07e10 against 0.81e10 q/s — a two-lane sub-warp (one 64-byte request per line) when the lines come out
+  // of HBM — C5: 5.0e9 against 3.3e9 q/s (tools/ab_count3_lanes.sh, tools/ab_lanes_ctas.sh)
+  const uint64_t count_set = (uint64_t)idx->view.L * idx->view.level_stride + idx->view.kmer_entries * sizeof(uint2);
+  const int lanes3 = idx->count3_lanes ? idx->count3_lanes : (count_set <= (96ull << 20) ? 1 : 2);
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_count3(a, lanes3)
                            : nib ? idx->num_sms * max_blocks_per_sm_count2(tma, idx->view, a) : persistent_grid(idx, (const void*)count_kernel);
-  const uint64_t want = (npat * (dna ? 2 : 4) + kThreads - 1) / kThreads;
+  const uint64_t want = (npat * (dna ? lanes3 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   // Two-pass form on an index with text sections: one query per thread for everything that finishes in "lookup,
@@ -389,7 +394,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   } else {
     if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
     if (dna)
-      launch_count3(idx->view, a, grid, stream);
+      launch_count3(idx->view, a, grid, stream, lanes3);
     else if (nib)
       launch_count2(idx->view, a, grid, stream, tma);
     else
@@ -501,14 +506,19 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   w.lf_total = (idx->instr_mask & 1u) ? ctr + 1 : nullptr;
   const bool nib = idx->view.layout == kLayoutNibble128;
   const bool dna = idx->view.layout == kLayoutDna64;
-  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_walk3()
+  // layout 3: one lane per row while the walk's working set (level lines + samples) is within reach of the L2 — measured
+  // on C4 (123 MB, half of the fetches hit the L2): 3.48e9 against 3.05e9 occ/s — a two-lane sub-warp (one 64-byte
+  // request per line) when the lines come out of HBM (tools/ab_walk3_lanes.sh, tools/ab_lanes_ctas.sh)
+  const uint64_t walk_set = (uint64_t)idx->view.L * idx->view.level_stride + (uint64_t)idx->view.nsamp * 4;
+  const int lanes3 = idx->walk3_lanes ? idx->walk3_lanes : (walk_set <= (160ull << 20) ? 1 : 2);
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_walk3(lanes3)
                            : nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
-  const uint64_t want = (count * (dna ? 2 : 4) + kThreads - 1) / kThreads;
+  const uint64_t want = (count * (dna ? lanes3 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
   const bool timed = (idx->instr_mask & 2u) != 0;
   if (timed) CSFM_CUDA(cudaEventRecord(idx->ev0, stream));
   if (dna)
-    launch_walk3(idx->view, w, grid, stream);
+    launch_walk3(idx->view, w, grid, stream, lanes3);
   else if (nib)
     launch_walk2(idx->view, w, grid, stream);
   else

@@ -28,8 +28,8 @@ __device__ __forceinline__ void rank_pair3(const uint8_t* __restrict__ lv, uint3
   const bool load = active && !special;
   const bool split = load && (le != ls);
   Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
-  if (load) { check_line(iv, lv + (size_t)ls * kLine3Bytes, 32); ks = ldg_nc_v8(lv + (size_t)ls * kLine3Bytes); }
-  if (split) { check_line(iv, lv + (size_t)le * kLine3Bytes, 32); ke = ldg_nc_v8(lv + (size_t)le * kLine3Bytes); }
+  if (load) { check_line(iv, lv + (size_t)ls * kLine3Bytes, 32); ks = ldg_line_keep(lv + (size_t)ls * kLine3Bytes); }
+  if (split) { check_line(iv, lv + (size_t)le * kLine3Bytes, 32); ke = ldg_line_keep(lv + (size_t)le * kLine3Bytes); }
   DnaHits xs = dna_hits(ks, v);
   const uint32_t cs = dna_counter(ks, v, h);
   const uint32_t ps = dna_partial(cs, xs, os, h);
@@ -55,14 +55,60 @@ __device__ __forceinline__ void rank_pair3(const uint8_t* __restrict__ lv, uint3
   }
 }
 
+// The same for ONE lane per query (count3_kernel<., 1>, indexes that live in the L2): the lane loads the whole 64-byte
+// line itself (two 256-bit loads) and needs no shuffle; a warp carries 32 queries, so everything around the rank (loop
+// control, refill, step set-up, address arithmetic) costs half the warp instructions per query. Out of HBM this form
+// would spend two fetch slots per line (profiles/README.md §R2.3), so it is used only while the index fits the L2.
+__device__ __forceinline__ void rank_pair3t(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp, uint32_t ep, bool active,
+                                            uint32_t px, uint32_t& rs, uint32_t& re, const IndexView& iv) {
+  const bool special = v == kSpecialCode;
+  const uint32_t ls = dna_line_of(sp), le = dna_line_of(ep);
+  const uint32_t os = sp - ls * kSymsPerLine3, oe = ep - le * kSymsPerLine3;
+  const bool load = active && !special;
+  const bool split = load && (le != ls);
+  Chunk32 A = chunk_undefined(), B = chunk_undefined();
+  if (load) {
+    check_line(iv, lv + (size_t)ls * kLine3Bytes, 64);
+    A = ldg_line_keep(lv + (size_t)ls * kLine3Bytes);
+    B = ldg_line_keep(lv + (size_t)ls * kLine3Bytes + 32);
+  }
+  uint32_t x[6], cnt;
+  dna_line_hits(A, B, v, x, cnt);
+  rs = dna_line_rank(cnt, x, os);
+  re = dna_line_rank(cnt, x, oe);
+  if (__any_sync(0xFFFFFFFFu, split)) {  // warp-uniform: rare once the intervals are narrower than a line
+    if (split) {
+      check_line(iv, lv + (size_t)le * kLine3Bytes, 64);
+      A = ldg_line_keep(lv + (size_t)le * kLine3Bytes);
+      B = ldg_line_keep(lv + (size_t)le * kLine3Bytes + 32);
+    }
+    uint32_t y[6], c2;
+    dna_line_hits(A, B, v, y, c2);
+    const uint32_t r2 = dna_line_rank(c2, y, oe);
+    re = split ? r2 : re;
+  }
+  const uint32_t zero = v == 0u ? 1u : 0u;  // the symbol that occurs once is stored (and counted) as a 0
+  rs -= zero & (sp > px ? 1u : 0u);
+  re -= zero & (ep > px ? 1u : 0u);
+  if (special) {
+    rs = sp > px ? 1u : 0u;
+    re = ep > px ? 1u : 0u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // count (fm_index.cpp:79-101)
 // ------------------------------------------------------------------------------------------
 #ifndef CSFM_COUNT3_CTAS
 #define CSFM_COUNT3_CTAS 6  // measured on C2: 6 (40 registers, no spill) beats 8 by 4 %
 #endif
-template <bool kInstr>
-__global__ void __launch_bounds__(kThreads, CSFM_COUNT3_CTAS)
+#ifndef CSFM_COUNT3T_CTAS
+#define CSFM_COUNT3T_CTAS 4  // measured on C2: 1.076 / 1.070 / 1.081 / 0.651e10 q/s at 3 / 4 / 5 / 6 (6 spills)
+#endif
+// kLanes = 2: a two-lane sub-warp per query (16 per warp, one 64-byte request per line: any index size);
+// kLanes = 1: one lane per query (32 per warp: indexes that fit the L2).
+template <bool kInstr, int kLanes>
+__global__ void __launch_bounds__(kThreads, kLanes == 2 ? CSFM_COUNT3_CTAS : CSFM_COUNT3T_CTAS)
 count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ uint32_t sC[257];
   __shared__ uint2 step_tab[256];  // x = C[byte], y = compact code | (byte absent) << 31
@@ -72,7 +118,8 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
-  const int h = lane & 1;
+  const int h = kLanes == 2 ? (lane & 1) : 0;
+  const bool leader = h == 0;  // the lane that writes the query's results
   const uint8_t* const lv = iv.levels + h * 32;
   const uint32_t px = iv.special_row;
   const uint32_t kk = iv.kmer_k;
@@ -86,7 +133,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   uint32_t my_steps = 0, my_lookups = 0, my_lines = 0;
 
   auto finish = [&](uint32_t cnt, uint32_t lo, uint32_t hi) {
-    if (h == 0) {
+    if (leader) {
       if (a.counts) a.counts[q] = cnt;
       if (a.sp_ep) {
         a.sp_ep[2 * (uint64_t)q] = lo;
@@ -112,7 +159,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
   };
 
   for (;;) {
-    const uint32_t item = queue_take32g<2>(wq, !active, lane, a.cursor, (uint32_t)a.npat);
+    const uint32_t item = queue_take32g<kLanes>(wq, !active, lane, a.cursor, (uint32_t)a.npat);
     if (item != ~0u) {
       q = item;
       const uint64_t o0 = a.offs[q], o1 = a.offs[(uint64_t)q + 1];
@@ -121,7 +168,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
       active = true;
       if (m == 0) {
         // count("") == n (fm_index.cpp:80); locate("") is empty (fm_index.cpp:109)
-        if (h == 0) {
+        if (leader) {
           if (a.counts) a.counts[q] = iv.n;
           if (a.sp_ep) { a.sp_ep[2 * (uint64_t)q] = 0; a.sp_ep[2 * (uint64_t)q + 1] = 0; }
           if (a.row_sp) { a.row_sp[q] = 0; a.row_cnt[q] = 0; }
@@ -148,7 +195,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
         } else if (keyed) {
           if (kInstr) ++my_lookups;
           CSFM_CHK(e < iv.kmer_entries, "k-mer key inside the table");
-          const uint2 se = iv.kmer[e];
+          const uint2 se = ldg_table_keep(&iv.kmer[e]);
           sp = se.x;
           ep = se.y;
           if (sp >= ep) {
@@ -183,7 +230,8 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     // ---- one backward-search step: sp/ep <- C[c] + rank(c, .)  (fm_index.cpp:92-93)
     if (kInstr && active && code != kSpecialCode) my_lines += 1u + (dna_line_of(sp) != dna_line_of(ep) ? 1u : 0u);
     uint32_t rs, re;
-    rank_pair3(lv, code, sp, ep, active, h, px, rs, re, iv);
+    if constexpr (kLanes == 2) rank_pair3(lv, code, sp, ep, active, h, px, rs, re, iv);
+    else rank_pair3t(lv, code, sp, ep, active, px, rs, re, iv);
     if (active) {
       sp = base + rs;
       ep = base + re;
@@ -198,7 +246,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     }
   }
   if (kInstr && a.steps_total) {
-    unsigned s = (h == 0) ? my_steps : 0, t = (h == 0) ? my_lookups : 0, w = (h == 0) ? my_lines : 0;
+    unsigned s = leader ? my_steps : 0, t = leader ? my_lookups : 0, w = leader ? my_lines : 0;
     for (int o = 16; o > 0; o >>= 1) {
       s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
       t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
@@ -254,9 +302,30 @@ __device__ __forceinline__ uint32_t access_rank3(const uint8_t* __restrict__ lv,
                                                  uint32_t& v, const IndexView& iv) {
   Chunk32 k = chunk_undefined();
   const uint32_t line = dna_line_of(p), off = p - line * kSymsPerLine3;
-  if (active) { check_line(iv, lv + (size_t)line * kLine3Bytes, 32); k = ldg_nc_v8(lv + (size_t)line * kLine3Bytes); }
+  if (active) { check_line(iv, lv + (size_t)line * kLine3Bytes, 32); k = ldg_line_keep(lv + (size_t)line * kLine3Bytes); }
   v = __shfl_sync(0xFFFFFFFFu, dna_symbol(k, off, h), (lane & ~1) | (off >= 96u ? 1 : 0));
   return group2_sum(dna_partial(dna_counter(k, v, h), dna_hits(k, v), off, h));
+}
+
+// The same for one LANE per row (walk3_kernel<1>): the lane loads both halves of the line, no shuffles.
+__device__ __forceinline__ uint32_t access_rank3t(const uint8_t* __restrict__ lv, uint32_t p, bool active, uint32_t& v,
+                                                  const IndexView& iv) {
+  Chunk32 A = chunk_undefined(), B = chunk_undefined();
+  const uint32_t line = dna_line_of(p), off = p - line * kSymsPerLine3;
+  if (active) {
+    check_line(iv, lv + (size_t)line * kLine3Bytes, 64);
+    A = ldg_line_keep(lv + (size_t)line * kLine3Bytes);
+    B = ldg_line_keep(lv + (size_t)line * kLine3Bytes + 32);
+  }
+  // the symbol at off: half A holds symbols 0..95, half B 96..191
+  const bool in_b = off >= 96u;
+  const uint32_t loff = off - (in_b ? 96u : 0u), t = loff >> 5, sft = loff & 31u;
+  const uint32_t lo = in_b ? pick4(B.c2, B.p0, B.p2, B.p2, t) : pick4(A.c2, A.p0, A.p2, A.p2, t);
+  const uint32_t hi = in_b ? pick4(B.c3, B.p1, B.p3, B.p3, t) : pick4(A.c3, A.p1, A.p3, A.p3, t);
+  v = ((lo >> sft) & 1u) | (((hi >> sft) & 1u) << 1);
+  uint32_t x[6], cnt;
+  dna_line_hits(A, B, v, x, cnt);
+  return dna_line_rank(cnt, x, off);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -265,13 +334,18 @@ __device__ __forceinline__ uint32_t access_rank3(const uint8_t* __restrict__ lv,
 #ifndef CSFM_WALK3_CTAS
 #define CSFM_WALK3_CTAS 6
 #endif
-__global__ void __launch_bounds__(kThreads, CSFM_WALK3_CTAS)
+#ifndef CSFM_WALK3T_CTAS
+#define CSFM_WALK3T_CTAS 6  // measured on C4: 3.37 / 3.33 / 3.28 / 3.48e9 occ/s at 3 / 4 / 5 / 6 (39 registers; 7 spills)
+#endif
+// kLanes = 2: a two-lane sub-warp per row (one 64-byte request per line); kLanes = 1: one lane per row (32 walks per warp)
+template <int kLanes>
+__global__ void __launch_bounds__(kThreads, kLanes == 2 ? CSFM_WALK3_CTAS : CSFM_WALK3T_CTAS)
 walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
   __shared__ uint32_t base_by_code[8];
   if (threadIdx.x < 8) base_by_code[threadIdx.x] = iv.hdr->base_by_code[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int h = lane & 1;
+  const int h = kLanes == 2 ? (lane & 1) : 0;
   const uint8_t* const lv = iv.levels + h * 32;
   const uint32_t px = iv.special_row;
   WarpQueue wq;
@@ -302,15 +376,15 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
     }
     CSFM_CHK(k < iv.nsamp, "sample index inside the sampled suffix array");
     if (h == 0) {
-      uint64_t pos = (uint64_t)iv.ssa[k] + steps;  // fm_index.cpp:147-152
+      uint64_t pos = (uint64_t)ldg_once_u32(&iv.ssa[k]) + steps;  // fm_index.cpp:147-152
       if (pos >= iv.n) pos -= iv.n;                // sa_val < n and steps < n
-      a.out_pos[slot] = pos;
+      stg_once_u64(&a.out_pos[slot], pos);
     }
     active = false;
   };
 
   for (;;) {
-    const unsigned long long item = queue_takeg<2>(wq, !active, lane, a.cursor, a.total);
+    const unsigned long long item = queue_takeg<kLanes>(wq, !active, lane, a.cursor, a.total);
     if (item != ~0ull) {
       slot = a.first + item;
       start = a.rows_implicit ? a.row_base + (uint32_t)slot : (uint32_t)a.out_pos[slot];
@@ -323,7 +397,9 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
 
     // ---- one LF step: LF(i) = C[c] + occ(c, i)  (fm_index.hpp:62-66)
     uint32_t v;
-    const uint32_t r = access_rank3(lv, p, active, lane, h, v, iv);
+    uint32_t r;
+    if constexpr (kLanes == 2) r = access_rank3(lv, p, active, lane, h, v, iv);
+    else r = access_rank3t(lv, p, active, v, iv);
     if (active) {
       // row px holds the symbol that occurs once: LF(px) = C[that symbol] + 0
       const uint32_t row = p == px ? iv.special_first : base_by_code[v] + r - ((v == 0u && p > px) ? 1u : 0u);
@@ -420,12 +496,18 @@ int blocks_per_sm3(const void* kernel) {
 
 }  // namespace
 
-void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream) {
-  if (a.steps_total) count3_kernel<true><<<grid, kThreads, 0, stream>>>(iv, a);
-  else count3_kernel<false><<<grid, kThreads, 0, stream>>>(iv, a);
+void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, int lanes) {
+  if (lanes == 1) {
+    if (a.steps_total) count3_kernel<true, 1><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count3_kernel<false, 1><<<grid, kThreads, 0, stream>>>(iv, a);
+  } else {
+    if (a.steps_total) count3_kernel<true, 2><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count3_kernel<false, 2><<<grid, kThreads, 0, stream>>>(iv, a);
+  }
 }
-void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream) {
-  walk3_kernel<<<grid, kThreads, 0, stream>>>(iv, a);
+void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream, int lanes) {
+  if (lanes == 1) walk3_kernel<1><<<grid, kThreads, 0, stream>>>(iv, a);
+  else walk3_kernel<2><<<grid, kThreads, 0, stream>>>(iv, a);
 }
 void launch_untext3(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms,
                     cudaStream_t stream) {
@@ -436,10 +518,14 @@ void launch_untext3(const IndexView& iv, uint8_t* out, unsigned long long* curso
 void launch_access3(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
   access3_kernel<<<grid, kThreads, 0, stream>>>(iv, out);
 }
-int max_blocks_per_sm_count3(const CountArgs& a) {
-  return a.steps_total ? blocks_per_sm3((const void*)count3_kernel<true>) : blocks_per_sm3((const void*)count3_kernel<false>);
+int max_blocks_per_sm_count3(const CountArgs& a, int lanes) {
+  if (lanes == 1)
+    return a.steps_total ? blocks_per_sm3((const void*)count3_kernel<true, 1>) : blocks_per_sm3((const void*)count3_kernel<false, 1>);
+  return a.steps_total ? blocks_per_sm3((const void*)count3_kernel<true, 2>) : blocks_per_sm3((const void*)count3_kernel<false, 2>);
 }
-int max_blocks_per_sm_walk3() { return blocks_per_sm3((const void*)walk3_kernel); }
+int max_blocks_per_sm_walk3(int lanes) {
+  return lanes == 1 ? blocks_per_sm3((const void*)walk3_kernel<1>) : blocks_per_sm3((const void*)walk3_kernel<2>);
+}
 int max_blocks_per_sm_access3() { return blocks_per_sm3((const void*)access3_kernel); }
 
 int build_kmer_table3(csfm_index* idx, cudaStream_t stream) {

@@ -203,10 +203,15 @@ def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
     (4, 383, 7, "middle", 0x7F), (4, 384, 7, "end", 0x7F), (4, 385, 1, "start", 0x7F), (2, 5_000, 16, None, 0), (4, 97, 32, None, 0),
     (1, 700, 9, "end", 0x00),
 ])
-def test_dna_layout_vs_oracle(fm, letters, n, stride, where, single):
-    """Layout 3 (two-bit symbols, 64-byte lines, two-lane sub-warps): <= 4 frequent symbols plus one symbol that
+@pytest.mark.parametrize("lanes", ["1", "2"])
+def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where, single):
+    """Layout 3 (two-bit symbols, 64-byte lines): <= 4 frequent symbols plus one symbol that
     occurs once ANYWHERE in the text and anywhere in byte order (not only a smallest terminator), line-boundary
-    sizes (192 symbols per line), failing LF walks, every build product, counts, intervals, positions."""
+    sizes (192 symbols per line), failing LF walks, every build product, counts, intervals, positions. Both forms of
+    the count and walk kernels: one lane per query / row (the default while the index fits the L2) and a two-lane
+    sub-warp (the default beyond); the knobs are read when a handle is created."""
+    monkeypatch.setenv("CSFM_COUNT3_LANES", lanes)
+    monkeypatch.setenv("CSFM_WALK3_LANES", lanes)
     rng = np.random.default_rng(letters * 7919 + n + stride)
     alpha = np.array([0x41, 0x43, 0x47, 0x54][:letters], dtype=np.uint8)
     body = alpha[rng.integers(0, letters, n)].astype(np.uint8)
