@@ -534,7 +534,8 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
     out = {"metric": "locate occurrences/sec", "value": total_all / t_s, "unit": "occurrences/s", "n_gpus": world,
            "ms_per_batch": ms, "scaling": "weak",
            "config": {"workload": f"C4: 2^{n_log2} B DNA+$ text, ssa_stride 32, {npat} text-sampled patterns len {plen} per GPU, limit {limit}",
-                      "levels": L, "line_bytes": lb, "layout": int(info.layout), "index_bytes": int(info.blob_bytes),
+                      "levels": L, "line_bytes": lb, "layout": int(info.layout), "position_samples": int(info.position_samples),
+                      "index_bytes": int(info.blob_bytes),
                       "walk_working_set_bytes": walk_set, "kmer_k": int(info.kmer_k), "index_build_s": build_s,
                       "index_broadcast_ms": bcast_ms},
            "occurrences_per_batch": int(total_all), "lf_steps_per_occurrence": lf_all / max(1, total_all),
@@ -589,15 +590,19 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
         # occurrence at text position p ends at the nearest sampled position at or before p (cyclically), so
         # its length is the distance to it. The sum must equal the LF steps the walk kernel counted.
         try:
-            sa = torch.as_tensor(_DevMem(idx_sa.sa_device_ptr(), 4 * n), device=dev).view(torch.int32)  # n < 2^31 here
-            sampled = sa[::32].to(torch.int64)                 # SA[k * stride]: the positions whose rows are sampled
-            mark = torch.full((n,), -1, dtype=torch.int64, device=dev)
-            mark[sampled] = sampled
-            prev = torch.cummax(mark, 0).values               # nearest sampled position <= q, -1 if none
-            del mark
-            pp = prev[d_pos]
-            wl = torch.where(pp >= 0, d_pos - pp, d_pos + (n - int(sampled.max())))
-            del prev, pp
+            if int(info.position_samples):
+                # marked form: the samples sit at the text positions that are multiples of the stride
+                wl = d_pos % 32
+            else:
+                sa = torch.as_tensor(_DevMem(idx_sa.sa_device_ptr(), 4 * n), device=dev).view(torch.int32)  # n < 2^31 here
+                sampled = sa[::32].to(torch.int64)                 # SA[k * stride]: the positions whose rows are sampled
+                mark = torch.full((n,), -1, dtype=torch.int64, device=dev)
+                mark[sampled] = sampled
+                prev = torch.cummax(mark, 0).values               # nearest sampled position <= q, -1 if none
+                del mark
+                pp = prev[d_pos]
+                wl = torch.where(pp >= 0, d_pos - pp, d_pos + (n - int(sampled.max())))
+                del prev, pp
             edges = [0, 1, 8, 16, 32, 64, 128, 256]
             hist = torch.bincount(torch.bucketize(wl, torch.tensor(edges[1:], device=dev), right=True), minlength=len(edges))
             out["walk_lengths"] = {"mean": float(wl.double().mean()), "max": int(wl.max()),
@@ -1166,7 +1171,7 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "n": n, "levels": L, "line_bytes": int(info.line_bytes), "layout": int(info.layout),
+        "config": {"workload": wl["desc"], "n": n, "levels": L, "line_bytes": int(info.line_bytes), "layout": int(info.layout), "position_samples": int(info.position_samples),
                    "sigma": int(info.sigma), "batch_per_gpu": batch,
                    "distinct_batches": NB, "index_bytes": int(info.blob_bytes), "parallelism": f"dp{world} (index replicated)",
                    "l2_policy": f"inputs larger than L2: {info.blob_bytes / 1e9:.2f} GB index + a different batch every step" if not in_l2

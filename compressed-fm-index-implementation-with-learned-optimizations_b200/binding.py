@@ -25,6 +25,7 @@ Q_OK, Q_LF_WALK_EXCEEDED, Q_SSA_OOB = 0, 1, 2
 BUILD_DEFAULT, BUILD_NO_COMPACT, BUILD_KEEP_SA, BUILD_LAYOUT_BINARY64, BUILD_NO_KMER_TABLE, BUILD_NO_TEXT_CHECK, BUILD_FORCE_TEXT_CHECK = 0, 1, 2, 4, 8, 16, 32
 BUILD_LARGE_TABLE = 64
 BUILD_LAYOUT_NIBBLE128 = 128
+BUILD_ROW_SAMPLES = 256
 
 LF_WALK_MESSAGE = "locate: LF walk exceeded text length"  # fm_index.cpp:137
 
@@ -50,7 +51,8 @@ class IndexInfo(C.Structure):
                 ("device", C.c_uint32), ("nsamp", C.c_uint64), ("blocks_per_level", C.c_uint64),
                 ("blob_bytes", C.c_uint64), ("has_sa", C.c_uint32), ("layout", C.c_uint32), ("line_bytes", C.c_uint32),
                 ("kmer_k", C.c_uint32), ("text_check", C.c_uint32), ("half_table", C.c_uint32),
-                ("sa_rounds", C.c_uint32), ("sa_radix_passes", C.c_uint32), ("sa_pair_passes", C.c_uint64)]
+                ("sa_rounds", C.c_uint32), ("sa_radix_passes", C.c_uint32), ("sa_pair_passes", C.c_uint64),
+                ("position_samples", C.c_uint32), ("pad0", C.c_uint32)]
 
 
 class CallStats(C.Structure):

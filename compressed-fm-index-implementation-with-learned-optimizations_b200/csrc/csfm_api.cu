@@ -267,6 +267,7 @@ int csfm_info(const csfm_index* idx, csfm_index_info* out) {
   out->sa_rounds = idx->sa_rounds;
   out->sa_radix_passes = idx->sa_radix_passes;
   out->sa_pair_passes = idx->sa_pair_passes;
+  out->position_samples = idx->h.layout == kLayoutDna64 && idx->h.marked;
   return CSFM_OK;
 }
 
@@ -393,7 +394,10 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
   if (std::memcmp(h.magic, "CSFMDEV1", 8) != 0 || h.version != 3) return fail(CSFM_ERR_FORMAT, "bad blob magic/version");
   const bool nib = h.layout == kLayoutNibble128;
   const bool dna = h.layout == kLayoutDna64;
-  const uint64_t per_line = dna ? kSymsPerLine3 : nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
+  const uint64_t per_line = dna ? (h.marked ? kSymsPerLine3M : kSymsPerLine3) : nib ? kSymsPerLine : kPayloadBits, line_bytes = nib ? kLine2Bytes : kLineBytes;
+  if (h.marked > 1 || (h.marked && !dna) || (h.marked != 0) != (h.off_psamp != 0) ||
+      (h.marked && (h.off_psamp % 4 || h.off_psamp < h.off_ssa + h.nsamp * 4 || h.off_psamp > h.total_bytes || h.nsamp * 4 > h.total_bytes - h.off_psamp)))
+    return fail(CSFM_ERR_FORMAT, "inconsistent position samples in blob header");
   if ((h.layout != kLayoutNibble128 && h.layout != kLayoutBinary64 && h.layout != kLayoutDna64) || h.total_bytes > bytes || h.levels == 0 ||
       h.levels > (nib ? 2u : dna ? 1u : kMaxLevels) || h.nblk != h.n / per_line + 1 || h.off_levels < sizeof(BlobHeader) ||
       h.off_ssa + h.nsamp * 4 > h.total_bytes || h.stride == 0 ||
@@ -410,6 +414,7 @@ int csfm_attach_blob(void* d_blob, uint64_t bytes, int device, int take_ownershi
     for (uint32_t i = 0; i < h.kmer_k && entries <= (1ull << 40); ++i) entries *= h.kmer_radix;
     const uint64_t table_bytes = h.kmer_tiled ? (entries + 1) * 4 : entries * 8;
     if (!(nib || dna) || (dna && (h.kmer_tiled || h.off_kmer_hi)) || h.kmer_k > 16 || h.kmer_radix < 2 || h.kmer_radix > 256 || h.off_kmer < h.off_ssa + h.nsamp * 4 ||
+        (h.marked && h.off_kmer < h.off_psamp + h.nsamp * 4) ||
         h.kmer_tiled > 1 || (h.kmer_tiled && !h.off_text) || h.off_kmer + table_bytes > h.total_bytes)
       return fail(CSFM_ERR_FORMAT, "inconsistent k-mer table in blob header");
     if (h.off_kmer_hi && (h.levels != 2 || h.off_kmer_hi < h.off_kmer + table_bytes || h.off_kmer_hi + entries * 128 > h.total_bytes))

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "csfm_dna.cuh"
 #include "csfm_host.hpp"
@@ -214,11 +215,19 @@ nib_split_kernel(const uint8_t* __restrict__ cur, uint8_t* __restrict__ nxt, uin
 __device__ __forceinline__ uint32_t dna_word_of_pair(uint32_t t) { return 8u * (t / 3u) + 2u + 2u * (t % 3u); }
 __device__ __forceinline__ uint32_t dna_word_of_counter(uint32_t v) { return 8u * (v >> 1) + (v & 1u); }
 
-// One warp per line: the six (lo, hi) pairs + the per-line histogram linecnt[v * nblk + b]. `cur` holds compact
-// codes; the symbol that occurs once (code 4) is stored and counted as a 0.
+// the marked form (csfm_dna.cuh): pairs 0..3, two per half, then the half's two mark words; counters c0 c1 | c2 marks
+__device__ __forceinline__ uint32_t dna_word_of_pair_m(uint32_t t) { return 8u * (t >> 1) + 2u + 2u * (t & 1u); }
+__device__ __forceinline__ uint32_t dna_word_of_marks_m(uint32_t t) { return 8u * (t >> 1) + 6u + (t & 1u); }
+__device__ __forceinline__ uint32_t dna_word_of_counter_m(uint32_t v) { return v < 2u ? v : 6u + v; }  // 0, 1, 8, 9
+
+// One warp per line: the (lo, hi) pairs + the per-line histogram linecnt[v * nblk + b]. `cur` holds compact
+// codes; the symbol that occurs once (code 4) is stored and counted as a 0. Marked form (kM): 128 rows per line, a
+// mark bit for every row whose suffix starts at a multiple of the sample stride, and their number in slot v = 3
+// (the counter of v = 3 is implied there).
+template <bool kM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 dna_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, uint8_t* __restrict__ level, uint64_t nblk,
-                uint32_t* __restrict__ linecnt) {
+                uint32_t* __restrict__ linecnt, const uint32_t* __restrict__ sa, uint32_t stride) {
   const int lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -226,8 +235,8 @@ dna_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, uint8_t* __restrict
     uint32_t* line = reinterpret_cast<uint32_t*>(level + b * kLine3Bytes);
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-    for (uint32_t t = 0; t < 6; ++t) {
-      const uint64_t i = b * kSymsPerLine3 + 32 * t + lane;
+    for (uint32_t t = 0; t < (kM ? 4u : 6u); ++t) {
+      const uint64_t i = b * Line3<kM>::kSyms + 32 * t + lane;
       const bool valid = i < n;
       uint32_t v = valid ? cur[i] : 0u;
       if (v >= 4u) v = 0u;
@@ -236,25 +245,42 @@ dna_pack_kernel(const uint8_t* __restrict__ cur, uint64_t n, uint8_t* __restrict
       c0 += __popc(~lo & ~hi & in);
       c1 += __popc(lo & ~hi & in);
       c2 += __popc(~lo & hi & in);
-      c3 += __popc(lo & hi & in);
-      if (lane == 0) {
-        line[dna_word_of_pair(t)] = lo;
-        line[dna_word_of_pair(t) + 1] = hi;
+      if constexpr (kM) {
+        const uint32_t mk = __ballot_sync(0xFFFFFFFFu, valid && sa[i] % stride == 0u);
+        c3 += __popc(mk);
+        if (lane == 0) {
+          line[dna_word_of_pair_m(t)] = lo;
+          line[dna_word_of_pair_m(t) + 1] = hi;
+          line[dna_word_of_marks_m(t)] = mk;
+        }
+      } else {
+        c3 += __popc(lo & hi & in);
+        if (lane == 0) {
+          line[dna_word_of_pair(t)] = lo;
+          line[dna_word_of_pair(t) + 1] = hi;
+        }
       }
     }
     if (lane < 4) linecnt[(uint64_t)lane * nblk + b] = lane == 0 ? c0 : lane == 1 ? c1 : lane == 2 ? c2 : c3;
   }
 }
 
+template <bool kM>
 __global__ void dna_counters_kernel(uint8_t* __restrict__ level, uint64_t nblk, const uint32_t* __restrict__ prefix) {
   const uint64_t total = nblk * 4;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
     const uint64_t b = t >> 2;
     const uint32_t v = (uint32_t)(t & 3);
-    reinterpret_cast<uint32_t*>(level + b * kLine3Bytes)[dna_word_of_counter(v)] = prefix[(uint64_t)v * nblk + b];
+    reinterpret_cast<uint32_t*>(level + b * kLine3Bytes)[kM ? dna_word_of_counter_m(v) : dna_word_of_counter(v)] = prefix[(uint64_t)v * nblk + b];
   }
 }
+
+// the position samples of the marked form: the SA values that are multiples of the stride, in row order
+struct IsPositionSample {
+  uint32_t stride;
+  __device__ __forceinline__ bool operator()(const uint32_t& s) const { return s % stride == 0u; }
+};
 
 // row of the one occurrence of `byte` in the BWT
 __global__ void find_byte_kernel(const uint8_t* __restrict__ data, uint64_t n, uint8_t byte, unsigned int* __restrict__ row) {
@@ -403,6 +429,9 @@ int index_finish_handle(csfm_index* idx) {
   v.special_row = h.layout == kLayoutDna64 ? h.special_row : kNoSpecialRow;
   v.special_byte = h.special_byte;
   v.special_first = h.C[h.special_byte & 0xFFu];
+  v.marked = (h.layout == kLayoutDna64 && h.marked && h.off_psamp) ? 1u : 0u;
+  v.psamp = v.marked ? reinterpret_cast<const uint32_t*>(idx->d_blob + h.off_psamp) : nullptr;
+  v.pad1 = 0;
   v.kmer = h.kmer_k ? reinterpret_cast<const uint2*>(idx->d_blob + h.off_kmer) : nullptr;
   v.kmer_k = h.kmer_k;
   v.kmer_radix = h.kmer_radix;
@@ -498,11 +527,25 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   const uint32_t L = h.levels;
   const bool nib = h.layout == kLayoutNibble128;
   const bool dna = h.layout == kLayoutDna64;
-  h.nblk = dna ? n / kSymsPerLine3 + 1 : nib ? n / kSymsPerLine + 1 : n / kPayloadBits + 1;
+  // layout 3, marked form (csfm_dna.cuh): suffix-array samples by text position, found through a mark bit per row. Needs
+  // the suffix array at hand and SA[LF(r)] = SA[r] - 1 for every row but the one of suffix 0, i.e. a text whose LAST byte
+  // occurs exactly once (any byte value; with five symbols it is the one without a two-bit code); other texts keep the
+  // reference's row-sampled walk (and its failure semantics).
+  bool marked = false;
+  if (dna && n >= 2 && d_text && d_sa && !(flags & CSFM_BUILD_ROW_SAMPLES) && !std::getenv("CSFM_NO_POSITION_SAMPLES")) {
+    uint8_t last = 0;
+    marked = cudaMemcpy(&last, d_text + (n - 1), 1, cudaMemcpyDeviceToHost) == cudaSuccess && hist[last] == 1;
+  }
+  h.marked = marked ? 1u : 0u;
+  h.nblk = dna ? n / (marked ? kSymsPerLine3M : kSymsPerLine3) + 1 : nib ? n / kSymsPerLine + 1 : n / kPayloadBits + 1;
   h.off_levels = kHeaderBytes;
   h.level_stride = align_up(h.nblk * (nib ? kLine2Bytes : kLineBytes), 256);  // layouts 1 and 3: 64-byte lines
   h.off_ssa = h.off_levels + (uint64_t)L * h.level_stride;
   h.total_bytes = align_up(h.off_ssa + nsamp * 4, 256);
+  if (marked) {
+    h.off_psamp = h.total_bytes;
+    h.total_bytes = align_up(h.off_psamp + nsamp * 4, 256);
+  }
   // k-mer jump table: the first k steps of a query become one lookup. Budget: a quarter of the
   // level bytes, between 1 MiB and 1 GiB (k = 3 for a byte alphabet at n = 2^30, 9 for DNA+$ at 2^26,
   // 11 for DNA+$ at 4e9).
@@ -629,11 +672,31 @@ int index_from_device_bwt(const uint8_t* d_bwt, uint64_t n, const uint32_t* d_ss
   const int grid = (int)std::min<uint64_t>(want_blocks, 148ull * 64);
   if (dna) {
     uint8_t* level = idx->d_blob + h.off_levels;
-    dna_pack_kernel<<<grid, wpb * 32, 0, st>>>(d_cur, n, level, h.nblk, d_pop);
+    if (h.marked) dna_pack_kernel<true><<<grid, wpb * 32, 0, st>>>(d_cur, n, level, h.nblk, d_pop, d_sa, h.stride);
+    else dna_pack_kernel<false><<<grid, wpb * 32, 0, st>>>(d_cur, n, level, h.nblk, d_pop, nullptr, 1u);
     for (int v = 0; v < 4; ++v)
       BUILD_CUDA(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_tmp_bytes, d_pop + (uint64_t)v * h.nblk,
                                                d_rank + (uint64_t)v * h.nblk, (int64_t)h.nblk, st));
-    dna_counters_kernel<<<2048, 256, 0, st>>>(level, h.nblk, d_rank);
+    if (h.marked) dna_counters_kernel<true><<<2048, 256, 0, st>>>(level, h.nblk, d_rank);
+    else dna_counters_kernel<false><<<2048, 256, 0, st>>>(level, h.nblk, d_rank);
+    if (h.marked) {
+      // position samples: SA values that are multiples of the stride, in row order (d_pop is free again: its first
+      // 8 bytes take the number selected)
+      void* d_sel_tmp = nullptr;
+      size_t sel_bytes = 0;
+      uint32_t* const psamp = reinterpret_cast<uint32_t*>(idx->d_blob + h.off_psamp);
+      unsigned long long* const d_nsel = reinterpret_cast<unsigned long long*>(d_pop);
+      const IsPositionSample pred{h.stride};
+      BUILD_CUDA(cub::DeviceSelect::If(nullptr, sel_bytes, d_sa, psamp, d_nsel, (int64_t)n, pred, st));
+      BUILD_CUDA(cudaMalloc(&d_sel_tmp, sel_bytes ? sel_bytes : 16));
+      cudaError_t se = cub::DeviceSelect::If(d_sel_tmp, sel_bytes, d_sa, psamp, d_nsel, (int64_t)n, pred, st);
+      unsigned long long nsel = 0;
+      if (se == cudaSuccess) se = cudaMemcpyAsync(&nsel, d_nsel, 8, cudaMemcpyDeviceToHost, st);
+      if (se == cudaSuccess) se = cudaStreamSynchronize(st);
+      cudaFree(d_sel_tmp);
+      BUILD_CUDA(se);
+      if (nsel != nsamp) return bail(CSFM_ERR_CUDA, "position samples: the suffix array is not a permutation of 0..n-1");
+    }
     if (h.code_of_byte[h.special_byte & 0xFFu] == kSpecialCode) {
       // the row of the symbol that occurs once (d_pop is free again: borrow its first word)
       BUILD_CUDA(cudaMemsetAsync(d_pop, 0xFF, 4, st));

@@ -91,7 +91,9 @@ struct BlobHeader {
   // ends in a unique smallest byte: rows are then sorted rotations, the intervals of all k-mers tile
   // [0, n) in key order, and the table is the prefix sum of the text's (cyclic) k-gram histogram.
   uint32_t kmer_tiled;
-  uint32_t reserved0[1];
+  // layout 3: 1 = the MARKED line form (csfm_dna.cuh: 128 rows per line with a mark bit each, suffix array sampled by text
+  // position at off_psamp, nsamp entries) beside the row-sampled array of the reference's format at off_ssa
+  uint32_t marked;
   uint32_t start1[16];         // layout 2: first position of hi-group g in level 1
   // byte-indexed tables
   uint32_t C[257];             // fm_index.cpp:36-47
@@ -103,6 +105,8 @@ struct BlobHeader {
   uint32_t base_by_code[256];  // same, indexed by compact code (LF step)
   uint8_t code_of_byte[256];   // compact code, 0 for absent bytes (absence <=> C[b+1]==C[b])
   uint8_t byte_of_code[256];
+  uint64_t off_psamp;          // marked form: psamp[k] = SA value of the k-th marked row (u32), 0 = absent
+  uint64_t reserved1;
 };
 static_assert(sizeof(BlobHeader) % 16 == 0, "header must stay 16-byte aligned");
 constexpr uint64_t kHeaderBytes = 4096;
@@ -136,6 +140,9 @@ struct IndexView {
   uint32_t special_first;  // layout 3: C[special byte] = the row LF maps special_row to
   uint32_t special_byte;
   uint64_t kmer_entries;   // keys of the k-mer table (radix ^ k), 0 = no table
+  const uint32_t* psamp;   // layout 3, marked form: SA values of the marked rows in row order, else nullptr
+  uint32_t marked;         // layout 3: the lines are in the marked form
+  uint32_t pad1;
   uint32_t zeros[kMaxLevels];
 };
 

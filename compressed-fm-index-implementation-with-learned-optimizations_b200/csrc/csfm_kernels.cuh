@@ -324,11 +324,11 @@ int max_blocks_per_sm_access2();
 void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, int lanes);  // lanes per query: 2, or 1 for L2-resident indexes
 void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream, int lanes);
 void launch_access3(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream);
-int max_blocks_per_sm_count3(const CountArgs& a, int lanes);
+int max_blocks_per_sm_count3(const IndexView& iv, const CountArgs& a, int lanes);
 // the text back out of the index (extract without a text section): every sampled row walks LF to the next one
 void launch_untext2(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms, cudaStream_t stream);
 void launch_untext3(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms, cudaStream_t stream);
-int max_blocks_per_sm_walk3(int lanes);
-int max_blocks_per_sm_access3();
+int max_blocks_per_sm_walk3(const IndexView& iv, int lanes);
+int max_blocks_per_sm_access3(const IndexView& iv);
 
 }  // namespace csfm

@@ -349,7 +349,7 @@ int count_device(csfm_index* idx, const uint8_t* d_bytes, const uint64_t* d_offs
   // of HBM — C5: 5.0e9 against 3.3e9 q/s (tools/ab_count3_lanes.sh, tools/ab_lanes_ctas.sh)
   const uint64_t count_set = (uint64_t)idx->view.L * idx->view.level_stride + idx->view.kmer_entries * sizeof(uint2);
   const int lanes3 = idx->count3_lanes ? idx->count3_lanes : (count_set <= (96ull << 20) ? 1 : 2);
-  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_count3(a, lanes3)
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_count3(idx->view, a, lanes3)
                            : nib ? idx->num_sms * max_blocks_per_sm_count2(tma, idx->view, a) : persistent_grid(idx, (const void*)count_kernel);
   const uint64_t want = (npat * (dna ? lanes3 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
@@ -507,11 +507,12 @@ int locate_walk(csfm_index* idx, uint64_t npat, const uint64_t* d_out_offs, uint
   const bool nib = idx->view.layout == kLayoutNibble128;
   const bool dna = idx->view.layout == kLayoutDna64;
   // layout 3: one lane per row while the walk's working set (level lines + samples) is within reach of the L2 — measured
-  // on C4 (123 MB, half of the fetches hit the L2): 3.48e9 against 3.05e9 occ/s — a two-lane sub-warp (one 64-byte
-  // request per line) when the lines come out of HBM (tools/ab_walk3_lanes.sh, tools/ab_lanes_ctas.sh)
+  // on C4: 3.3e9 against 3.05e9 occ/s with row samples (123 MB), 5.5e9 against 4.1e9 with position samples (168 MB) — a
+  // two-lane sub-warp (one 64-byte request per line) when the lines come out of HBM (tools/ab_walk3_lanes.sh,
+  // tools/ab_lanes_ctas.sh, tools/ab_position_samples.sh)
   const uint64_t walk_set = (uint64_t)idx->view.L * idx->view.level_stride + (uint64_t)idx->view.nsamp * 4;
-  const int lanes3 = idx->walk3_lanes ? idx->walk3_lanes : (walk_set <= (160ull << 20) ? 1 : 2);
-  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_walk3(lanes3)
+  const int lanes3 = idx->walk3_lanes ? idx->walk3_lanes : (walk_set <= (256ull << 20) ? 1 : 2);
+  const int grid_max = dna ? idx->num_sms * max_blocks_per_sm_walk3(idx->view, lanes3)
                            : nib ? idx->num_sms * max_blocks_per_sm_walk2() : persistent_grid(idx, (const void*)walk_kernel);
   const uint64_t want = (count * (dna ? lanes3 : 4) + kThreads - 1) / kThreads;
   const int grid = (int)std::min<uint64_t>(want, (uint64_t)grid_max);
@@ -548,7 +549,7 @@ int extract_bwt_device(csfm_index* idx, uint8_t* d_out, cudaStream_t stream) {
   const bool dna = idx->view.layout == kLayoutDna64;
   int per_sm = 0;
   if (dna)
-    per_sm = max_blocks_per_sm_access3();
+    per_sm = max_blocks_per_sm_access3(idx->view);
   else if (nib)
     per_sm = max_blocks_per_sm_access2();
   else

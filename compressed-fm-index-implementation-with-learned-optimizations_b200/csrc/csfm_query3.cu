@@ -20,29 +20,31 @@ namespace {
 
 // rank(v, sp) and rank(v, ep) in the one level of the index. lv = level base + 32 * h. All 32 lanes call it.
 // v == kSpecialCode (the symbol that occurs once, at BWT row px): occ(v, p) = (p > px), no memory access.
+template <bool kM>
 __device__ __forceinline__ void rank_pair3(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp, uint32_t ep, bool active,
                                            int h, uint32_t px, uint32_t& rs, uint32_t& re, const IndexView& iv) {
+  constexpr uint32_t kSyms = Line3<kM>::kSyms;
   const bool special = v == kSpecialCode;
-  const uint32_t ls = dna_line_of(sp), le = dna_line_of(ep);
-  const uint32_t os = sp - ls * kSymsPerLine3, oe = ep - le * kSymsPerLine3;
+  const uint32_t ls = dna_line_of_t<kM>(sp), le = dna_line_of_t<kM>(ep);
+  const uint32_t os = sp - ls * kSyms, oe = ep - le * kSyms;
   const bool load = active && !special;
   const bool split = load && (le != ls);
   Chunk32 ks = chunk_undefined(), ke = chunk_undefined();
   if (load) { check_line(iv, lv + (size_t)ls * kLine3Bytes, 32); ks = ldg_line_keep(lv + (size_t)ls * kLine3Bytes); }
   if (split) { check_line(iv, lv + (size_t)le * kLine3Bytes, 32); ke = ldg_line_keep(lv + (size_t)le * kLine3Bytes); }
-  DnaHits xs = dna_hits(ks, v);
-  const uint32_t cs = dna_counter(ks, v, h);
-  const uint32_t ps = dna_partial(cs, xs, os, h);
+  DnaHits xs = dna_hits<kM>(ks, v);
+  const uint32_t cs = dna_counter<kM>(ks, v, h, ls * kSyms);
+  const uint32_t ps = dna_partial<kM>(cs, xs, os, h);
   uint32_t ce = cs;
   if (__any_sync(0xFFFFFFFFu, split)) {  // warp-uniform: skipped once every interval is narrower than a line
-    const DnaHits x2 = dna_hits(ke, v);
-    const uint32_t c2 = dna_counter(ke, v, h);
+    const DnaHits x2 = dna_hits<kM>(ke, v);
+    const uint32_t c2 = dna_counter<kM>(ke, v, h, le * kSyms);
     xs.h0 = split ? x2.h0 : xs.h0;
     xs.h1 = split ? x2.h1 : xs.h1;
     xs.h2 = split ? x2.h2 : xs.h2;
     ce = split ? c2 : cs;
   }
-  const uint32_t pe = dna_partial(ce, xs, oe, h);
+  const uint32_t pe = dna_partial<kM>(ce, xs, oe, h);
   rs = group2_sum(ps);
   re = group2_sum(pe);
   // the symbol that occurs once is stored (and counted) as a 0: rank(0, p) is one too high beyond its row
@@ -59,11 +61,13 @@ __device__ __forceinline__ void rank_pair3(const uint8_t* __restrict__ lv, uint3
 // line itself (two 256-bit loads) and needs no shuffle; a warp carries 32 queries, so everything around the rank (loop
 // control, refill, step set-up, address arithmetic) costs half the warp instructions per query. Out of HBM this form
 // would spend two fetch slots per line (profiles/README.md §R2.3), so it is used only while the index fits the L2.
+template <bool kM>
 __device__ __forceinline__ void rank_pair3t(const uint8_t* __restrict__ lv, uint32_t v, uint32_t sp, uint32_t ep, bool active,
                                             uint32_t px, uint32_t& rs, uint32_t& re, const IndexView& iv) {
+  constexpr uint32_t kSyms = Line3<kM>::kSyms;
   const bool special = v == kSpecialCode;
-  const uint32_t ls = dna_line_of(sp), le = dna_line_of(ep);
-  const uint32_t os = sp - ls * kSymsPerLine3, oe = ep - le * kSymsPerLine3;
+  const uint32_t ls = dna_line_of_t<kM>(sp), le = dna_line_of_t<kM>(ep);
+  const uint32_t os = sp - ls * kSyms, oe = ep - le * kSyms;
   const bool load = active && !special;
   const bool split = load && (le != ls);
   Chunk32 A = chunk_undefined(), B = chunk_undefined();
@@ -73,9 +77,9 @@ __device__ __forceinline__ void rank_pair3t(const uint8_t* __restrict__ lv, uint
     B = ldg_line_keep(lv + (size_t)ls * kLine3Bytes + 32);
   }
   uint32_t x[6], cnt;
-  dna_line_hits(A, B, v, x, cnt);
-  rs = dna_line_rank(cnt, x, os);
-  re = dna_line_rank(cnt, x, oe);
+  dna_line_hits<kM>(A, B, v, x, cnt, ls * kSyms);
+  rs = dna_line_rank<kM>(cnt, x, os);
+  re = dna_line_rank<kM>(cnt, x, oe);
   if (__any_sync(0xFFFFFFFFu, split)) {  // warp-uniform: rare once the intervals are narrower than a line
     if (split) {
       check_line(iv, lv + (size_t)le * kLine3Bytes, 64);
@@ -83,8 +87,8 @@ __device__ __forceinline__ void rank_pair3t(const uint8_t* __restrict__ lv, uint
       B = ldg_line_keep(lv + (size_t)le * kLine3Bytes + 32);
     }
     uint32_t y[6], c2;
-    dna_line_hits(A, B, v, y, c2);
-    const uint32_t r2 = dna_line_rank(c2, y, oe);
+    dna_line_hits<kM>(A, B, v, y, c2, le * kSyms);
+    const uint32_t r2 = dna_line_rank<kM>(c2, y, oe);
     re = split ? r2 : re;
   }
   const uint32_t zero = v == 0u ? 1u : 0u;  // the symbol that occurs once is stored (and counted) as a 0
@@ -107,7 +111,7 @@ __device__ __forceinline__ void rank_pair3t(const uint8_t* __restrict__ lv, uint
 #endif
 // kLanes = 2: a two-lane sub-warp per query (16 per warp, one 64-byte request per line: any index size);
 // kLanes = 1: one lane per query (32 per warp: indexes that fit the L2).
-template <bool kInstr, int kLanes>
+template <bool kInstr, int kLanes, bool kM>
 __global__ void __launch_bounds__(kThreads, kLanes == 2 ? CSFM_COUNT3_CTAS : CSFM_COUNT3T_CTAS)
 count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ CountArgs a) {
   __shared__ uint32_t sC[257];
@@ -228,10 +232,10 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
     // ---- one backward-search step: sp/ep <- C[c] + rank(c, .)  (fm_index.cpp:92-93)
-    if (kInstr && active && code != kSpecialCode) my_lines += 1u + (dna_line_of(sp) != dna_line_of(ep) ? 1u : 0u);
+    if (kInstr && active && code != kSpecialCode) my_lines += 1u + (dna_line_of_t<kM>(sp) != dna_line_of_t<kM>(ep) ? 1u : 0u);
     uint32_t rs, re;
-    if constexpr (kLanes == 2) rank_pair3(lv, code, sp, ep, active, h, px, rs, re, iv);
-    else rank_pair3t(lv, code, sp, ep, active, px, rs, re, iv);
+    if constexpr (kLanes == 2) rank_pair3<kM>(lv, code, sp, ep, active, h, px, rs, re, iv);
+    else rank_pair3t<kM>(lv, code, sp, ep, active, px, rs, re, iv);
     if (active) {
       sp = base + rs;
       ep = base + re;
@@ -260,6 +264,7 @@ count3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ Coun
 
 // Fills the k-mer jump table by running the same backward search over every k-symbol string:
 // entry e decodes to codes d_0 (LAST character, e % radix), d_1, ... and stores its interval.
+template <bool kM>
 __global__ void __launch_bounds__(kThreads)
 kmer_build3_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ table, unsigned long long entries, uint32_t k,
                    uint32_t radix) {
@@ -288,7 +293,7 @@ kmer_build3_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tab
       byte = byte_of_code[code];
       const bool act = alive && (sC[byte + 1] != sC[byte]);
       uint32_t rs, re;
-      rank_pair3(lv, code, sp, ep, act, h, px, rs, re, iv);
+      rank_pair3<kM>(lv, code, sp, ep, act, h, px, rs, re, iv);
       sp = sC[byte] + rs;
       ep = sC[byte] + re;
       alive = act && sp < ep;
@@ -297,35 +302,52 @@ kmer_build3_kernel(const __grid_constant__ IndexView iv, uint2* __restrict__ tab
   }
 }
 
-// One LF step's memory access: the symbol at row p and its rank before p, from ONE line.
+// One LF step's memory access: the symbol at row p and its rank before p, from ONE line. Marked form: also the mark bit
+// of row p and the number of marked rows before it (the index of its position sample).
+template <bool kM>
 __device__ __forceinline__ uint32_t access_rank3(const uint8_t* __restrict__ lv, uint32_t p, bool active, int lane, int h,
-                                                 uint32_t& v, const IndexView& iv) {
+                                                 uint32_t& v, const IndexView& iv, uint32_t* mark = nullptr, uint32_t* mrank = nullptr) {
+  constexpr uint32_t kSyms = Line3<kM>::kSyms;
   Chunk32 k = chunk_undefined();
-  const uint32_t line = dna_line_of(p), off = p - line * kSymsPerLine3;
+  const uint32_t line = dna_line_of_t<kM>(p), off = p - line * kSyms;
   if (active) { check_line(iv, lv + (size_t)line * kLine3Bytes, 32); k = ldg_line_keep(lv + (size_t)line * kLine3Bytes); }
-  v = __shfl_sync(0xFFFFFFFFu, dna_symbol(k, off, h), (lane & ~1) | (off >= 96u ? 1 : 0));
-  return group2_sum(dna_partial(dna_counter(k, v, h), dna_hits(k, v), off, h));
+  const int owner = (lane & ~1) | (off >= Line3<kM>::kHalf ? 1 : 0);
+  if constexpr (kM) {
+    // symbol and mark bit travel in one shuffle
+    const uint32_t got = __shfl_sync(0xFFFFFFFFu, dna_symbol<true>(k, off, h) | (dna_mark(k, off, h) << 2), owner);
+    v = got & 3u;
+    if (mark) {
+      *mark = got >> 2;
+      *mrank = group2_sum(dna_mark_partial(k, off, h));
+    }
+  } else {
+    v = __shfl_sync(0xFFFFFFFFu, dna_symbol<false>(k, off, h), owner);
+  }
+  return group2_sum(dna_partial<kM>(dna_counter<kM>(k, v, h, line * kSyms), dna_hits<kM>(k, v), off, h));
 }
 
-// The same for one LANE per row (walk3_kernel<1>): the lane loads both halves of the line, no shuffles.
+// The same for one LANE per row (walk3_kernel<1, .>): the lane loads both halves of the line, no shuffles.
+template <bool kM>
 __device__ __forceinline__ uint32_t access_rank3t(const uint8_t* __restrict__ lv, uint32_t p, bool active, uint32_t& v,
-                                                  const IndexView& iv) {
+                                                  const IndexView& iv, uint32_t* mark = nullptr, uint32_t* mrank = nullptr) {
+  constexpr uint32_t kSyms = Line3<kM>::kSyms;
   Chunk32 A = chunk_undefined(), B = chunk_undefined();
-  const uint32_t line = dna_line_of(p), off = p - line * kSymsPerLine3;
+  const uint32_t line = dna_line_of_t<kM>(p), off = p - line * kSyms;
   if (active) {
     check_line(iv, lv + (size_t)line * kLine3Bytes, 64);
     A = ldg_line_keep(lv + (size_t)line * kLine3Bytes);
     B = ldg_line_keep(lv + (size_t)line * kLine3Bytes + 32);
   }
-  // the symbol at off: half A holds symbols 0..95, half B 96..191
-  const bool in_b = off >= 96u;
-  const uint32_t loff = off - (in_b ? 96u : 0u), t = loff >> 5, sft = loff & 31u;
-  const uint32_t lo = in_b ? pick4(B.c2, B.p0, B.p2, B.p2, t) : pick4(A.c2, A.p0, A.p2, A.p2, t);
-  const uint32_t hi = in_b ? pick4(B.c3, B.p1, B.p3, B.p3, t) : pick4(A.c3, A.p1, A.p3, A.p3, t);
-  v = ((lo >> sft) & 1u) | (((hi >> sft) & 1u) << 1);
+  v = dna_line_symbol<kM>(A, B, off);
+  if constexpr (kM) {
+    if (mark) {
+      *mark = dna_line_mark(A, B, off);
+      *mrank = dna_line_mark_rank(A, B, off);
+    }
+  }
   uint32_t x[6], cnt;
-  dna_line_hits(A, B, v, x, cnt);
-  return dna_line_rank(cnt, x, off);
+  dna_line_hits<kM>(A, B, v, x, cnt, line * kSyms);
+  return dna_line_rank<kM>(cnt, x, off);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,7 +360,9 @@ __device__ __forceinline__ uint32_t access_rank3t(const uint8_t* __restrict__ lv
 #define CSFM_WALK3T_CTAS 6  // measured on C4: 3.37 / 3.33 / 3.28 / 3.48e9 occ/s at 3 / 4 / 5 / 6 (39 registers; 7 spills)
 #endif
 // kLanes = 2: a two-lane sub-warp per row (one 64-byte request per line); kLanes = 1: one lane per row (32 walks per warp)
-template <int kLanes>
+// kM: the marked line form — the walk ends at the first row whose suffix starts at a multiple of the stride (its mark bit
+// sits in the line the step fetches anyway): at most stride - 1 steps, SA[row] = sample + steps as before.
+template <int kLanes, bool kM>
 __global__ void __launch_bounds__(kThreads, kLanes == 2 ? CSFM_WALK3_CTAS : CSFM_WALK3T_CTAS)
 walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkArgs a) {
   __shared__ uint32_t base_by_code[8];
@@ -368,15 +392,15 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
     }
     active = false;
   };
-  auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]
-    const uint32_t k = sample_index(iv, row);
+  auto emit = [&](uint32_t row) {  // row is sampled: SA[row] = ssa[row/stride]; marked form: row = index of the position sample
+    const uint32_t k = kM ? row : sample_index(iv, row);
     if (k >= iv.nsamp) {  // fm_index.cpp:141-146 (unreachable for a consistent index)
       fail_walk((int)CSFM_Q_SSA_OOB);
       return;
     }
     CSFM_CHK(k < iv.nsamp, "sample index inside the sampled suffix array");
     if (h == 0) {
-      uint64_t pos = (uint64_t)ldg_once_u32(&iv.ssa[k]) + steps;  // fm_index.cpp:147-152
+      uint64_t pos = (uint64_t)ldg_once_u32(kM ? &iv.psamp[k] : &iv.ssa[k]) + steps;  // fm_index.cpp:147-152
       if (pos >= iv.n) pos -= iv.n;                // sa_val < n and steps < n
       stg_once_u64(&a.out_pos[slot], pos);
     }
@@ -391,21 +415,28 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
       steps = 0;
       active = true;
       p = start;
-      if (row_is_sampled(iv, start)) emit(start);
+      if constexpr (!kM)
+        if (row_is_sampled(iv, start)) emit(start);
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
 
     // ---- one LF step: LF(i) = C[c] + occ(c, i)  (fm_index.hpp:62-66)
-    uint32_t v;
+    uint32_t v, mk = 0, mr = 0;
     uint32_t r;
-    if constexpr (kLanes == 2) r = access_rank3(lv, p, active, lane, h, v, iv);
-    else r = access_rank3t(lv, p, active, v, iv);
-    if (active) {
+    if constexpr (kLanes == 2) r = access_rank3<kM>(lv, p, active, lane, h, v, iv, &mk, &mr);
+    else r = access_rank3t<kM>(lv, p, active, v, iv, &mk, &mr);
+    if (kM && active && mk) {
+      emit(mr);  // row p is marked: SA[p] = psamp[mr], the walk started `steps` positions further on
+    } else if (active) {
       // row px holds the symbol that occurs once: LF(px) = C[that symbol] + 0
       const uint32_t row = p == px ? iv.special_first : base_by_code[v] + r - ((v == 0u && p > px) ? 1u : 0u);
       ++steps;
       ++my_lf;
-      if (row_is_sampled(iv, row)) {
+      if (kM) {
+        // a consistent marked index ends every walk within stride - 1 steps; a corrupt one must not spin
+        if (steps >= iv.n) fail_walk((int)CSFM_Q_LF_WALK_EXCEEDED);
+        else p = row;
+      } else if (row_is_sampled(iv, row)) {
         emit(row);
       } else if (row == start || steps >= iv.n) {
         // LF is a permutation: back at the start without meeting a sampled row means the
@@ -424,6 +455,7 @@ walk3_kernel(const __grid_constant__ IndexView iv, const __grid_constant__ WalkA
 }
 
 // untext (see untext2_kernel in csfm_query2.cu): the text back out of the index, one two-lane sub-warp per sampled row
+template <bool kM>
 __global__ void __launch_bounds__(kThreads, 8)
 untext3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, unsigned long long* __restrict__ cursor,
                unsigned long long* __restrict__ written) {
@@ -451,7 +483,7 @@ untext3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, 
     }
     if (wq.exhausted && !__any_sync(0xFFFFFFFFu, active)) break;
     uint32_t v;
-    const uint32_t r = access_rank3(lv, p, active, lane, h, v, iv);
+    const uint32_t r = access_rank3<kM>(lv, p, active, lane, h, v, iv);
     if (active) {
       pos = pos == 0 ? iv.n - 1 : pos - 1;  // BWT[row] = T[(SA[row] - 1) mod n]  (bwt.hpp:10-13)
       if (h == 0) out[pos] = p == px ? (uint8_t)iv.special_byte : byte_of_code[v];
@@ -468,6 +500,7 @@ untext3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out, 
 // ------------------------------------------------------------------------------------------
 // access: BWT[i] for all i (wavelet.cpp:102-128) — verification / export, not a query path
 // ------------------------------------------------------------------------------------------
+template <bool kM>
 __global__ void __launch_bounds__(kThreads)
 access3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) {
   __shared__ uint8_t byte_of_code[8];
@@ -483,7 +516,7 @@ access3_kernel(const __grid_constant__ IndexView iv, uint8_t* __restrict__ out) 
     const uint64_t i = t * ngroups + group;
     const bool valid = i < iv.n;
     uint32_t v;
-    (void)access_rank3(lv, valid ? (uint32_t)i : 0u, valid, lane, h, v, iv);
+    (void)access_rank3<kM>(lv, valid ? (uint32_t)i : 0u, valid, lane, h, v, iv);
     if (valid && h == 0) out[i] = (uint32_t)i == iv.special_row ? (uint8_t)iv.special_byte : byte_of_code[v];
   }
 }
@@ -496,37 +529,58 @@ int blocks_per_sm3(const void* kernel) {
 
 }  // namespace
 
-void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, int lanes) {
+namespace {
+template <bool kM>
+const void* count3_fn(bool instr, int lanes) {
+  if (lanes == 1) return instr ? (const void*)count3_kernel<true, 1, kM> : (const void*)count3_kernel<false, 1, kM>;
+  return instr ? (const void*)count3_kernel<true, 2, kM> : (const void*)count3_kernel<false, 2, kM>;
+}
+template <bool kM>
+void launch_count3_t(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, int lanes) {
   if (lanes == 1) {
-    if (a.steps_total) count3_kernel<true, 1><<<grid, kThreads, 0, stream>>>(iv, a);
-    else count3_kernel<false, 1><<<grid, kThreads, 0, stream>>>(iv, a);
+    if (a.steps_total) count3_kernel<true, 1, kM><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count3_kernel<false, 1, kM><<<grid, kThreads, 0, stream>>>(iv, a);
   } else {
-    if (a.steps_total) count3_kernel<true, 2><<<grid, kThreads, 0, stream>>>(iv, a);
-    else count3_kernel<false, 2><<<grid, kThreads, 0, stream>>>(iv, a);
+    if (a.steps_total) count3_kernel<true, 2, kM><<<grid, kThreads, 0, stream>>>(iv, a);
+    else count3_kernel<false, 2, kM><<<grid, kThreads, 0, stream>>>(iv, a);
   }
 }
+template <bool kM>
+const void* walk3_fn(int lanes) { return lanes == 1 ? (const void*)walk3_kernel<1, kM> : (const void*)walk3_kernel<2, kM>; }
+}  // namespace
+
+void launch_count3(const IndexView& iv, const CountArgs& a, int grid, cudaStream_t stream, int lanes) {
+  if (iv.marked) launch_count3_t<true>(iv, a, grid, stream, lanes);
+  else launch_count3_t<false>(iv, a, grid, stream, lanes);
+}
 void launch_walk3(const IndexView& iv, const WalkArgs& a, int grid, cudaStream_t stream, int lanes) {
-  if (lanes == 1) walk3_kernel<1><<<grid, kThreads, 0, stream>>>(iv, a);
-  else walk3_kernel<2><<<grid, kThreads, 0, stream>>>(iv, a);
+  if (iv.marked) {
+    if (lanes == 1) walk3_kernel<1, true><<<grid, kThreads, 0, stream>>>(iv, a);
+    else walk3_kernel<2, true><<<grid, kThreads, 0, stream>>>(iv, a);
+  } else {
+    if (lanes == 1) walk3_kernel<1, false><<<grid, kThreads, 0, stream>>>(iv, a);
+    else walk3_kernel<2, false><<<grid, kThreads, 0, stream>>>(iv, a);
+  }
 }
 void launch_untext3(const IndexView& iv, uint8_t* out, unsigned long long* cursor, unsigned long long* written, int num_sms,
                     cudaStream_t stream) {
   const unsigned long long want = ((unsigned long long)iv.nsamp * 2 + kThreads - 1) / kThreads;
-  const int grid = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), (unsigned long long)num_sms * blocks_per_sm3((const void*)untext3_kernel));
-  untext3_kernel<<<grid, kThreads, 0, stream>>>(iv, out, cursor, written);
+  const void* fn = iv.marked ? (const void*)untext3_kernel<true> : (const void*)untext3_kernel<false>;
+  const int grid = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), (unsigned long long)num_sms * blocks_per_sm3(fn));
+  if (iv.marked) untext3_kernel<true><<<grid, kThreads, 0, stream>>>(iv, out, cursor, written);
+  else untext3_kernel<false><<<grid, kThreads, 0, stream>>>(iv, out, cursor, written);
 }
 void launch_access3(const IndexView& iv, uint8_t* out, int grid, cudaStream_t stream) {
-  access3_kernel<<<grid, kThreads, 0, stream>>>(iv, out);
+  if (iv.marked) access3_kernel<true><<<grid, kThreads, 0, stream>>>(iv, out);
+  else access3_kernel<false><<<grid, kThreads, 0, stream>>>(iv, out);
 }
-int max_blocks_per_sm_count3(const CountArgs& a, int lanes) {
-  if (lanes == 1)
-    return a.steps_total ? blocks_per_sm3((const void*)count3_kernel<true, 1>) : blocks_per_sm3((const void*)count3_kernel<false, 1>);
-  return a.steps_total ? blocks_per_sm3((const void*)count3_kernel<true, 2>) : blocks_per_sm3((const void*)count3_kernel<false, 2>);
+int max_blocks_per_sm_count3(const IndexView& iv, const CountArgs& a, int lanes) {
+  return blocks_per_sm3(iv.marked ? count3_fn<true>(a.steps_total != nullptr, lanes) : count3_fn<false>(a.steps_total != nullptr, lanes));
 }
-int max_blocks_per_sm_walk3(int lanes) {
-  return lanes == 1 ? blocks_per_sm3((const void*)walk3_kernel<1>) : blocks_per_sm3((const void*)walk3_kernel<2>);
+int max_blocks_per_sm_walk3(const IndexView& iv, int lanes) { return blocks_per_sm3(iv.marked ? walk3_fn<true>(lanes) : walk3_fn<false>(lanes)); }
+int max_blocks_per_sm_access3(const IndexView& iv) {
+  return blocks_per_sm3(iv.marked ? (const void*)access3_kernel<true> : (const void*)access3_kernel<false>);
 }
-int max_blocks_per_sm_access3() { return blocks_per_sm3((const void*)access3_kernel); }
 
 int build_kmer_table3(csfm_index* idx, cudaStream_t stream) {
   const BlobHeader& h = idx->h;
@@ -535,11 +589,13 @@ int build_kmer_table3(csfm_index* idx, cudaStream_t stream) {
   for (uint32_t i = 0; i < h.kmer_k; ++i) entries *= h.kmer_radix;
   uint2* table = reinterpret_cast<uint2*>(idx->d_blob + h.off_kmer);
   const unsigned long long want = (entries * 2 + kThreads - 1) / kThreads;
-  const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm3((const void*)kmer_build3_kernel));
   IndexView v = idx->view;  // the table is being written: the builder itself must not consult it
   v.kmer = nullptr;
   v.kmer_k = 0;
-  kmer_build3_kernel<<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
+  const void* fn = v.marked ? (const void*)kmer_build3_kernel<true> : (const void*)kmer_build3_kernel<false>;
+  const int grid = (int)std::min<unsigned long long>(want, (unsigned long long)idx->num_sms * blocks_per_sm3(fn));
+  if (v.marked) kmer_build3_kernel<true><<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
+  else kmer_build3_kernel<false><<<grid, kThreads, 0, stream>>>(v, table, entries, h.kmer_k, h.kmer_radix);
   CSFM_CUDA(cudaGetLastError());
   CSFM_CUDA(cudaStreamSynchronize(stream));
   return CSFM_OK;

@@ -101,6 +101,13 @@ typedef struct {
                                            bytes of layout 2, so configs[1] and configs[3] stay in the L2 */
 #define CSFM_BUILD_NO_KMER_TABLE 8u /* do not build the k-mer jump table (layout 2 builds one by
                                        default: the first k steps of a query become one lookup) */
+#define CSFM_BUILD_ROW_SAMPLES 256u /* layout 3: locate walks LF to a row-sampled suffix-array entry like the
+                                       reference (fm_index.cpp:125-153). By default, when the text's last byte is the
+                                       symbol that occurs once (DNA + terminator), csfm_build_from_text samples the
+                                       suffix array by TEXT POSITION as well — the same ceil(n / stride) samples, found
+                                       through one mark bit per row kept inside the level lines (128 rows per 64-byte
+                                       line instead of 192) — so a walk takes at most stride - 1 steps, half as many on
+                                       average; positions are SA[row] either way */
 
 typedef struct {
   uint64_t n;          /* text length (cs::IndexMeta::n, fm_index.hpp:15) */
@@ -125,6 +132,8 @@ typedef struct {
   uint64_t sa_pair_passes;  /* sum over all rounds of pairs sorted x 8-bit passes: the sort moved about
                                sa_pair_passes * 2 * 12 bytes. Rounds after the first sort only the suffixes whose
                                group still has more than one member once those are at most half of the text */
+  uint32_t position_samples; /* 1 = layout 3 in its marked form: locate walks to a suffix-array sample taken by text position */
+  uint32_t pad0;
 } csfm_index_info;
 
 /* Counters describing the most recent query call on this handle (for bench accounting). */

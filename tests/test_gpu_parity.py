@@ -193,7 +193,9 @@ def test_random_vs_oracle(fm, sigma, n, stride, term, flags, layout):
         assert (status == ostatus).all()
         ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
         assert (pos[ok] == opos[ok]).all()
-        if (ostatus == 0).all():
+        if idx.info().position_samples:  # layout 3, marked form: a walk takes SA[row] mod stride steps
+            assert (ostatus == 0).all() and lf_gpu == int((opos % stride).sum())
+        elif (ostatus == 0).all():
             assert lf_gpu == olf
 
 
@@ -222,6 +224,9 @@ def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where,
     idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=fm.BUILD_KEEP_SA)
     info = idx.info()
     assert info.layout == 3 and info.line_bytes == 64 and info.levels == 1
+    # the marked line form (suffix array sampled by text position) exactly when the last byte is the single symbol
+    assert info.position_samples == (1 if where == "end" else 0)
+    assert info.blocks_per_level == n // (128 if info.position_samples else 192) + 1
     orc = oracle.OracleIndex(text, stride=stride)
     assert (idx.sa() == orc.sa).all()
     assert (idx.bwt() == orc.bwt).all()          # access through the two-bit lines, incl. the row of the single symbol
@@ -237,9 +242,13 @@ def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where,
         pats.append(bytes([single, single]))
     d, o = fm.pack_patterns(pats)
     oc, ose, osteps = orc.count_batch(d, o, want_steps=True)
-    for build_flags in (0, fm.BUILD_NO_KMER_TABLE):
+    rows_only = None
+    for build_flags in (0, fm.BUILD_NO_KMER_TABLE, fm.BUILD_ROW_SAMPLES):
         ix = idx if build_flags == 0 else fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=build_flags)
         assert ix.info().layout == 3
+        if build_flags == fm.BUILD_ROW_SAMPLES:
+            rows_only = ix
+            assert ix.info().position_samples == 0 and (ix.ssa() == orc.ssa).all() and (ix.bwt() == orc.bwt).all()
         ix.set_instrumentation(1)
         counts, sp_ep = ix.count_batch(d, o, want_intervals=True)
         st = ix.last_call_stats()
@@ -252,16 +261,20 @@ def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where,
         ix.set_instrumentation(0)
         assert (ix.count_batch(d, o) == oc).all()   # the uninstrumented kernel
     for limit in (100000, 5):
-        idx.set_instrumentation(1)
-        offs, pos, status = idx.locate_batch(d, o, limit=limit)
-        lf_gpu = idx.last_call_stats().lf_steps
         ooffs, opos, ostatus, olf = orc.locate_batch(d, o, limit=limit)
-        assert (offs == ooffs).all()
-        assert (status == ostatus).all()
-        ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
-        assert (pos[ok] == opos[ok]).all()
-        if (ostatus == 0).all():
-            assert lf_gpu == olf
+        for ix in (idx, rows_only):
+            ix.set_instrumentation(1)
+            offs, pos, status = ix.locate_batch(d, o, limit=limit)
+            lf_gpu = ix.last_call_stats().lf_steps
+            assert (offs == ooffs).all()
+            assert (status == ostatus).all()
+            ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
+            assert (pos[ok] == opos[ok]).all()
+            if ix.info().position_samples:
+                # a walk ends at the first row whose suffix starts at a multiple of the stride: SA[row] mod stride steps
+                assert (ostatus == 0).all() and lf_gpu == int((opos % stride).sum())
+            elif (ostatus == 0).all():
+                assert lf_gpu == olf
     # the same answers from layout 2 on the same text, from a blob round trip, and one query at a time
     idx2 = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=fm.BUILD_LAYOUT_NIBBLE128)
     assert idx2.info().layout == 2
