@@ -283,3 +283,15 @@ def test_c4_locate_full_size(c4):
     offs2, pos2, status2 = _locate_device(idx_sa, bytes_d, offs_d, npat, 100000, dev)
     assert torch.equal(offs2, offs) and torch.equal(pos2, pos) and int(status2.max()) == 0
     idx_sa.close()
+    # the default index samples the suffix array by text position (marked lines, walks of at most stride - 1 steps); the
+    # reference's row-sampled walk (CSFM_BUILD_ROW_SAMPLES) gives the same positions in the same order
+    assert info.position_samples == 1 and info.blocks_per_level == n // 128 + 1
+    idx.set_instrumentation(1)
+    _locate_device(idx, bytes_d, offs_d, npat, 100000, dev)
+    assert idx.last_call_stats().lf_steps == int((pos % 32).sum())
+    idx.set_instrumentation(0)
+    rows = fm.FMIndex.build_from_text_device(text.data_ptr(), n, fm.BuildParams(ssa_stride=32), device=0, flags=fm.BUILD_ROW_SAMPLES)
+    assert rows.info().position_samples == 0 and rows.info().blocks_per_level == n // 192 + 1
+    offs3, pos3, status3 = _locate_device(rows, bytes_d, offs_d, npat, 100000, dev)
+    assert torch.equal(offs3, offs) and torch.equal(pos3, pos) and int(status3.max()) == 0
+    rows.close()
