@@ -288,6 +288,66 @@ def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where,
         assert idx.count(pats[q]) == int(oc[q])
 
 
+@pytest.mark.parametrize("letters,n,stride", [(4, 100_000, 32), (4, 128 * 37, 8), (4, 128 * 37 - 1, 3), (4, 129, 1), (3, 5_000, 7), (1, 300, 4)])
+def test_marked_lines_build_products(fm, letters, n, stride):
+    """The marked line form of layout 3 read back word by word (csrc/csfm_dna.cuh): 128 rows per 64-byte line, a mark bit
+    exactly at the rows whose suffix starts at a multiple of the stride, three counters + the mark counter before the
+    line, and the position samples = SA values of the marked rows in row order — against the oracle's SA and BWT."""
+    rng = np.random.default_rng(n + stride)
+    alpha = np.array([0x41, 0x43, 0x47, 0x54][:letters], dtype=np.uint8)
+    text = np.concatenate([alpha[rng.integers(0, letters, n - 1)], np.array([0x24], np.uint8)]).astype(np.uint8)
+    idx = fm.FMIndex.build_from_text(text, fm.BuildParams(ssa_stride=stride), flags=fm.BUILD_KEEP_SA)
+    info = idx.info()
+    assert info.layout == 3 and info.position_samples == 1
+    orc = oracle.OracleIndex(text, stride=stride)
+    sa = orc.sa.astype(np.int64)
+    nblk, nsamp = n // 128 + 1, (n + stride - 1) // stride
+    assert info.blocks_per_level == nblk and info.nsamp == nsamp
+    blob = idx.blob_to_host()
+    al = lambda x: (x + 255) // 256 * 256
+    off_levels = 4096
+    off_ssa = off_levels + al(nblk * 64)
+    off_psamp = al(off_ssa + nsamp * 4)
+    lines = blob[off_levels: off_levels + nblk * 64].view(np.uint32).reshape(nblk, 16)
+    # expected symbols: compact two-bit codes in byte order; with five symbols the terminator has none and is stored as 0
+    present = np.unique(text)
+    coded = present if present.size <= 4 else present[present != 0x24]
+    code = np.zeros(256, np.int64)
+    code[coded] = np.arange(coded.size)
+    sym = np.zeros(nblk * 128, np.int64)
+    sym[:n] = code[orc.bwt]
+    mark = np.zeros(nblk * 128, np.int64)
+    mark[:n] = (sa % stride == 0)
+    valid = np.zeros(nblk * 128, np.int64)
+    valid[:n] = 1
+    weights = (1 << np.arange(32, dtype=np.uint64))
+    def words(bits):  # [nblk, 4] u32 words of 32 rows each
+        return (bits.reshape(nblk, 4, 32).astype(np.uint64) * weights).sum(axis=2).astype(np.uint32)
+    lo, hi, mk = words(sym & 1), words(sym >> 1), words(mark)
+    for t in range(4):
+        base = 8 * (t >> 1)
+        assert (lines[:, base + 2 + 2 * (t & 1)] == lo[:, t]).all(), t
+        assert (lines[:, base + 3 + 2 * (t & 1)] == hi[:, t]).all(), t
+        assert (lines[:, base + 6 + (t & 1)] == mk[:, t]).all(), t
+    def before(bits):  # number of set entries before each line
+        per = bits.reshape(nblk, 128).sum(axis=1)
+        return (np.cumsum(per) - per).astype(np.uint32)
+    assert (lines[:, 0] == before((sym == 0) & (valid == 1))).all()
+    assert (lines[:, 1] == before(sym == 1)).all()
+    assert (lines[:, 8] == before(sym == 2)).all()
+    assert (lines[:, 9] == before(mark)).all()
+    psamp = blob[off_psamp: off_psamp + nsamp * 4].view(np.uint32)
+    assert (psamp == sa[sa % stride == 0]).all()          # boolean indexing keeps row order
+    assert (blob[off_ssa: off_ssa + nsamp * 4].view(np.uint32) == orc.ssa).all()   # the reference's row samples stay for export
+    # and every row walks to its own suffix: locate of all one-character patterns returns SA in row order
+    d, o = fm.pack_patterns([bytes([b]) for b in present])
+    offs, pos, status = idx.locate_batch(d, o, limit=n)
+    assert (status == 0).all() and int(offs[-1]) == n
+    C = orc.C.astype(np.int64)
+    for q, b in enumerate(present):
+        assert (pos[int(offs[q]): int(offs[q + 1])] == sa[C[b]: C[b + 1]]).all()
+
+
 @pytest.mark.parametrize("sigma,n,stride,flags", [(4, 70_000, 32, 0), (4, 70_000, 5, 128), (60, 90_000, 16, 0), (200, 50_000, 7, 32),
                                                   (3, 1_000, 1, 0), (255, 300, 4, 0)])
 def test_extract_from_the_index(fm, sigma, n, stride, flags):
