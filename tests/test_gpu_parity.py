@@ -284,6 +284,11 @@ def test_dna_layout_vs_oracle(fm, monkeypatch, lanes, letters, n, stride, where,
     c3, se3 = back.count_batch(d, o, want_intervals=True)
     assert (c3 == oc).all() and (se3 == ose).all()
     assert (back.bwt() == orc.bwt).all()
+    assert back.info().position_samples == info.position_samples      # the attached blob walks like the one it was copied from
+    ooffs, opos, ostatus, _ = orc.locate_batch(d, o, limit=9)
+    offs, pos, status = back.locate_batch(d, o, limit=9)
+    ok = np.repeat(ostatus == 0, np.diff(ooffs).astype(np.int64))
+    assert (offs == ooffs).all() and (status == ostatus).all() and (pos[ok] == opos[ok]).all()
     for q in range(0, len(pats), max(1, len(pats) // 40)):
         assert idx.count(pats[q]) == int(oc[q])
 
