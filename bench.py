@@ -258,10 +258,23 @@ def l2_random_peak(index_bytes, line_bytes):
         doc = json.load(open(os.path.join(ROOT, "profiles", "r2_l2_sweep_probe.json")))
         rows = [r for r in doc["results"] if r["ctas_per_sm"] == 8 and r["unit_bytes"] == line_bytes]
         rows.sort(key=lambda r: r["buffer_mib"])
+        prev = None
         for r in rows:
             if (r["buffer_mib"] << 20) >= index_bytes:
-                return float(r["gbytes_per_s"]), (f"measured: profiles/r2_l2_sweep_probe.json, {r['buffer_mib']} MiB working set, "
-                                                 f"{line_bytes}-byte units, {r['gunits_per_s']:.0f} G fetches/s")
+                if prev is None or (r["buffer_mib"] << 20) == index_bytes:
+                    return float(r["gbytes_per_s"]), (f"measured: profiles/r2_l2_sweep_probe.json, {r['buffer_mib']} MiB working set, "
+                                                     f"{line_bytes}-byte units, {r['gunits_per_s']:.0f} G fetches/s")
+                # between two rows of the sweep: linear in the working-set size (the rate falls steeply beyond the L2)
+                t = (index_bytes - (prev["buffer_mib"] << 20)) / float((r["buffer_mib"] - prev["buffer_mib"]) << 20)
+                gbs = prev["gbytes_per_s"] + t * (r["gbytes_per_s"] - prev["gbytes_per_s"])
+                gun = prev["gunits_per_s"] + t * (r["gunits_per_s"] - prev["gunits_per_s"])
+                return float(gbs), (f"measured: profiles/r2_l2_sweep_probe.json, interpolated between the {prev['buffer_mib']} and "
+                                    f"{r['buffer_mib']} MiB rows for a {index_bytes / 2**20:.0f} MiB working set, {line_bytes}-byte units, "
+                                    f"{gun:.0f} G fetches/s")
+            prev = r
+        if prev is not None:  # beyond the sweep: out of HBM the rate no longer depends on the size
+            return float(prev["gbytes_per_s"]), (f"measured: profiles/r2_l2_sweep_probe.json, {prev['buffer_mib']} MiB working set (the largest of "
+                                                f"the sweep), {line_bytes}-byte units, {prev['gunits_per_s']:.0f} G fetches/s")
     except Exception:
         pass
     return 144.0 * line_bytes, "fallback: 144 G random 128-byte fetches/s measured on a 32 MiB working set (round 1 probe)"

@@ -52,3 +52,12 @@ def test_working_set_ceilings_come_from_the_probe():
     assert "r2_l2_sweep_probe.json" in src
     assert small > mid > big > 0          # the fetch rate falls as the working set outgrows the L2
     assert bench.l2_random_peak(30 << 20, 128)[0] > bench.l2_random_peak(300 << 20, 128)[0]
+    # between two rows of the sweep the ceiling is interpolated, not taken from the next larger row; beyond the sweep the
+    # last row stands (out of HBM the rate no longer depends on the size)
+    lo, _ = bench.l2_random_peak(160 << 20, 64)
+    hi, _ = bench.l2_random_peak(192 << 20, 64)
+    between, src2 = bench.l2_random_peak(176 << 20, 64)
+    assert lo > between > hi and "interpolated" in src2
+    assert abs(between - (lo + hi) / 2) < 1e-6 * lo
+    beyond, src3 = bench.l2_random_peak(4 << 30, 64)
+    assert beyond == big and "largest" in src3
