@@ -280,6 +280,18 @@ def l2_random_peak(index_bytes, line_bytes):
     return 144.0 * line_bytes, "fallback: 144 G random 128-byte fetches/s measured on a 32 MiB working set (round 1 probe)"
 
 
+def count_working_set(info):
+    """Bytes a count call keeps coming back to: the level lines and the k-mer (+ half-step) table — not the suffix-array
+    samples, which only locate reads."""
+    ws = int(info.blocks_per_level) * int(info.line_bytes) * int(info.levels)
+    k = int(info.kmer_k)
+    if k:
+        radix = min(int(info.sigma), 4) if int(info.layout) == 3 else int(info.sigma)
+        entries = radix ** k
+        ws += entries * (4 if int(info.text_check) else 8) + (entries * 16 * 8 if int(info.half_table) else 0)
+    return ws
+
+
 def make_text(wl, n, device):
     from csfm_b200 import workloads as w
     return (w.byte_text_torch if wl["kind"] == "byte" else w.dna_text_torch)(n, wl["seed_text"], device)
@@ -1035,10 +1047,11 @@ def count_leg(args, wl_name, rank, world, local_rank, steps, warmup, full):
     traffic, traffic_meta = committed_traffic(args.workload if not args.large_table else args.workload + "_large_table", kernel_name)
     in_l2 = int(info.blob_bytes) <= L2_RESIDENT_BYTES
     if in_l2:
-        l2_peak, l2_src = l2_random_peak(int(info.blob_bytes), line_bytes)
+        l2_peak, l2_src = l2_random_peak(count_working_set(info), line_bytes)  # what the search touches: lines + table
         achieved = executed_bytes / t_launch_s / 1e9
         roofline = {"bound": "l2", "kernel": kernel_name, "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
                     "frac": achieved / l2_peak, "traffic": traffic, "peak_source": l2_src,
+                    "count_working_set_bytes": count_working_set(info),
                     "frac_basis": "executed line fetches x line bytes over the measured L2 random-fetch ceiling for a working set of this size",
                     "hbm_stream_peak": peak}
     else:

@@ -61,3 +61,13 @@ def test_working_set_ceilings_come_from_the_probe():
     assert abs(between - (lo + hi) / 2) < 1e-6 * lo
     beyond, src3 = bench.l2_random_peak(4 << 30, 64)
     assert beyond == big and "largest" in src3
+
+
+def test_count_working_set_is_lines_plus_table():
+    from types import SimpleNamespace as NS
+    # C2 in the marked form: 2^26 / 128 + 1 lines of 64 bytes, 4^11 entries of 8 bytes; the samples are not part of it
+    c2 = NS(blocks_per_level=(1 << 26) // 128 + 1, line_bytes=64, levels=1, kmer_k=11, sigma=5, layout=3, text_check=0, half_table=0)
+    assert bench.count_working_set(c2) == ((1 << 26) // 128 + 1) * 64 + 4 ** 11 * 8
+    # C3: two levels of 128-byte lines, 256^3 keys of 4 bytes (tiled table) and the half-step table
+    c3 = NS(blocks_per_level=(1 << 30) // 128 + 1, line_bytes=128, levels=2, kmer_k=3, sigma=256, layout=2, text_check=1, half_table=1)
+    assert bench.count_working_set(c3) == ((1 << 30) // 128 + 1) * 256 + 256 ** 3 * (4 + 128)
