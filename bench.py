@@ -526,8 +526,10 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
         return None
     L, lb = int(info.levels), int(info.line_bytes)
     # executed fetches are exact here: every LF step loads exactly L level lines, every occurrence one sample sector
-    # and writes 8 bytes (sum over occurrences of w x L x line + 32 + 8)
-    alg = lf_all * L * lb + total_all * 40
+    # and writes 8 bytes (sum over occurrences of w x L x line + 32 + 8). With position samples the walk also
+    # reads the line of the marked row it stops at (that is where the mark bit lives): w + 1 lines per occurrence.
+    line_loads = (lf_all + (total_all if int(info.position_samples) else 0)) * L
+    alg = line_loads * lb + total_all * 40
     peak, peak_src = measured_peak()
     t_s = ms / 1e3
     kname = {1: "walk_kernel", 2: "walk2_kernel", 3: "walk3_kernel"}.get(int(info.layout), "walk_kernel")
@@ -554,7 +556,7 @@ def measure_locate(fm, dev, rank=0, world=1, n_log2=28, npat=1_000_000, plen=10,
                 "random_fetch_ceiling_at_this_working_set_gbs": ws_peak, "frac_of_that_ceiling": achieved_exec / ws_peak,
                 "ceiling_source": ws_src}
     roof.update({"kernel": kname, "unit": "GB/s", "traffic": traffic, "traffic_capture": tmeta,
-                 "executed": {"bytes_per_batch": alg / world, "gbs": achieved_exec, "level_lines_per_s": lf_all * L / world / t_s},
+                 "executed": {"bytes_per_batch": alg / world, "gbs": achieved_exec, "level_lines_per_s": line_loads / world / t_s},
                  "note": "per GPU; time covers count pass + scan + expand + walk"})
     out = {"metric": "locate occurrences/sec", "value": total_all / t_s, "unit": "occurrences/s", "n_gpus": world,
            "ms_per_batch": ms, "scaling": "weak",

@@ -319,30 +319,12 @@ def test_marked_lines_build_products(fm, letters, n, stride):
     coded = present if present.size <= 4 else present[present != 0x24]
     code = np.zeros(256, np.int64)
     code[coded] = np.arange(coded.size)
-    sym = np.zeros(nblk * 128, np.int64)
-    sym[:n] = code[orc.bwt]
-    mark = np.zeros(nblk * 128, np.int64)
-    mark[:n] = (sa % stride == 0)
-    valid = np.zeros(nblk * 128, np.int64)
-    valid[:n] = 1
-    weights = (1 << np.arange(32, dtype=np.uint64))
-    def words(bits):  # [nblk, 4] u32 words of 32 rows each
-        return (bits.reshape(nblk, 4, 32).astype(np.uint64) * weights).sum(axis=2).astype(np.uint32)
-    lo, hi, mk = words(sym & 1), words(sym >> 1), words(mark)
-    for t in range(4):
-        base = 8 * (t >> 1)
-        assert (lines[:, base + 2 + 2 * (t & 1)] == lo[:, t]).all(), t
-        assert (lines[:, base + 3 + 2 * (t & 1)] == hi[:, t]).all(), t
-        assert (lines[:, base + 6 + (t & 1)] == mk[:, t]).all(), t
-    def before(bits):  # number of set entries before each line
-        per = bits.reshape(nblk, 128).sum(axis=1)
-        return (np.cumsum(per) - per).astype(np.uint32)
-    assert (lines[:, 0] == before((sym == 0) & (valid == 1))).all()
-    assert (lines[:, 1] == before(sym == 1)).all()
-    assert (lines[:, 8] == before(sym == 2)).all()
-    assert (lines[:, 9] == before(mark)).all()
+    from test_marked_model_cpu import marked_lines      # the numpy statement of the format (its walk is checked on the CPU)
+    want_lines, want_psamp = marked_lines(code[orc.bwt], sa, n, stride)
+    for w in range(16):
+        assert (lines[:, w] == want_lines[:, w]).all(), w
     psamp = blob[off_psamp: off_psamp + nsamp * 4].view(np.uint32)
-    assert (psamp == sa[sa % stride == 0]).all()          # boolean indexing keeps row order
+    assert (psamp == want_psamp).all() and (psamp == sa[sa % stride == 0]).all()          # boolean indexing keeps row order
     assert (blob[off_ssa: off_ssa + nsamp * 4].view(np.uint32) == orc.ssa).all()   # the reference's row samples stay for export
     # and every row walks to its own suffix: locate of all one-character patterns returns SA in row order
     d, o = fm.pack_patterns([bytes([b]) for b in present])
